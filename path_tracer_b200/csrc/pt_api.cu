@@ -1,0 +1,500 @@
+// pt_api.cu -- the C-ABI of include/pt_abi.h on top of the sm_100a kernel.
+//
+// There is no CPU path in this library: without a CUDA device every entry
+// point that would render returns PT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pt_abi.h"
+#include "pt_kernel.h"
+#include "pt_pack.h"
+#include "pt_packed.h"
+
+using namespace ptb;
+
+namespace {
+
+thread_local std::string g_error;
+int g_num_gpus = 1;
+pt_stats g_stats {};
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return PT_ERR_NO_DEVICE;
+  return PT_ERR_CUDA;
+}
+#define PT_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+constexpr int kCounterSlots = 64;
+
+}  // namespace
+
+// One uploaded scene: a single device arena holding the scan blob, the side
+// tables, materials, textures and the image byte pool (memory laid out once,
+// resident in HBM for as long as the handle lives).
+struct pt_device_scene {
+  int device = 0;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  SceneDesc desc {};
+  unsigned long long* queue_heads = nullptr;  // kCounterSlots work-queue heads
+  unsigned long long* counters = nullptr;     // [0] scans, [1] paths
+  int next_slot = 0;
+  unsigned long long paths_launched = 0;
+  LaunchInfo last_launch {};
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T> size_t place(std::vector<unsigned char>& host, const std::vector<T>& v) {
+  const size_t off = align_up(host.size(), 256);
+  host.resize(off + std::max<size_t>(v.size() * sizeof(T), 16));
+  if (!v.empty()) std::memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+  return off;
+}
+
+int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d_ms, uint64_t* h2d_bytes) {
+  if (!scene || !out) return fail(PT_ERR_INVALID_ARGUMENT, "pt_scene_upload: null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PT_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(PT_ERR_INVALID_ARGUMENT, "pt_scene_upload: bad device index");
+
+  PackedScene ps;
+  std::string err;
+  const int rc = pack_scene(*scene, ps, err);
+  if (rc != PT_OK) return fail(rc, err);
+
+  std::vector<unsigned char> host;
+  const size_t o_blob = place(host, ps.blob);
+  const size_t o_saux = place(host, ps.sphere_aux);
+  const size_t o_maux = place(host, ps.moving_aux);
+  const size_t o_raux = place(host, ps.rect_aux);
+  const size_t o_taux = place(host, ps.tri_aux);
+  const size_t o_baux = place(host, ps.box_aux);
+  const size_t o_media = place(host, ps.media);
+  const size_t o_mat = place(host, ps.materials);
+  const size_t o_tex = place(host, ps.textures);
+  const size_t o_heads = align_up(host.size(), 256);
+  host.resize(o_heads + sizeof(unsigned long long) * (kCounterSlots + 2), 0);
+  const size_t o_bytes = align_up(host.size(), 256);
+  const size_t tex_bytes = std::max<size_t>((size_t)scene->n_texture_bytes, 3);
+  const size_t total = o_bytes + align_up(tex_bytes, 256);
+
+  PT_CUDA(cudaSetDevice(device));
+  auto* ds = new pt_device_scene;
+  ds->device = device;
+  e = cudaMalloc(&ds->arena, total);
+  if (e != cudaSuccess) {
+    delete ds;
+    return cuda_fail(e, "cudaMalloc(scene arena)");
+  }
+  ds->arena_bytes = total;
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0), cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, 0);
+  e = cudaMemcpyAsync(ds->arena, host.data(), host.size(), cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess && scene->n_texture_bytes)
+    e = cudaMemcpyAsync(ds->arena + o_bytes, scene->texture_bytes, scene->n_texture_bytes, cudaMemcpyHostToDevice, 0);
+  else if (e == cudaSuccess)
+    e = cudaMemsetAsync(ds->arena + o_bytes, 0, 3, 0);
+  cudaEventRecord(ev1, 0);
+  if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0), cudaEventDestroy(ev1);
+  if (e != cudaSuccess) {
+    cudaFree(ds->arena);
+    delete ds;
+    return cuda_fail(e, "scene upload");
+  }
+  if (h2d_ms) *h2d_ms += ms;
+  if (h2d_bytes) *h2d_bytes += host.size() + scene->n_texture_bytes;
+
+  SceneDesc& d = ds->desc;
+  d.blob = ds->arena + o_blob;
+  d.blob_bytes = (uint32_t)ps.blob.size();
+  d.n_groups = ps.n_groups;
+  d.off_groups = ps.off_groups, d.off_sphere = ps.off_sphere, d.off_moving = ps.off_moving;
+  d.off_rect = ps.off_rect, d.off_triangle = ps.off_triangle, d.off_box = ps.off_box;
+  d.n_objects = ps.n_objects;
+  d.sphere_aux = reinterpret_cast<const SphereAux*>(ds->arena + o_saux);
+  d.moving_aux = reinterpret_cast<const SphereAux*>(ds->arena + o_maux);
+  d.rect_aux = reinterpret_cast<const ObjAux*>(ds->arena + o_raux);
+  d.tri_aux = reinterpret_cast<const TriAux*>(ds->arena + o_taux);
+  d.box_aux = reinterpret_cast<const ObjAux*>(ds->arena + o_baux);
+  d.media = reinterpret_cast<const MediumRec*>(ds->arena + o_media);
+  d.materials = ds->arena + o_mat;
+  d.textures = ds->arena + o_tex;
+  d.texture_bytes = ds->arena + o_bytes;
+  d.n_texture_texels = tex_bytes / 3;
+  d.n_materials = (uint32_t)ps.materials.size();
+  d.n_textures = (uint32_t)ps.textures.size();
+  ds->queue_heads = reinterpret_cast<unsigned long long*>(ds->arena + o_heads);
+  ds->counters = ds->queue_heads + kCounterSlots;
+  *out = ds;
+  return PT_OK;
+}
+
+int check_render_args(int width, int height, int spp, const pt_camera* cam, const pt_region* rg, const void* out) {
+  if (!cam || !rg || !out) return fail(PT_ERR_INVALID_ARGUMENT, "render: null argument");
+  if (width <= 0 || height <= 0 || spp <= 0) return fail(PT_ERR_INVALID_ARGUMENT, "render: width, height and spp must be positive");
+  if (rg->w < 0 || rg->h < 0 || rg->y_stride <= 0 || rg->x0 < 0 || rg->y0 < 0 || rg->x0 + rg->w > width ||
+      (rg->h > 0 && rg->y0 + (long long)(rg->h - 1) * rg->y_stride >= height))
+    return fail(PT_ERR_INVALID_ARGUMENT, "render: region outside the image");
+  return PT_OK;
+}
+
+// rows first, first+stride, ... of a `height`-row image
+pt_region rows_of(int width, int height, int first, int stride) {
+  pt_region r;
+  r.x0 = 0, r.y0 = first, r.w = width, r.y_stride = stride;
+  r.h = first < height ? (height - first + stride - 1) / stride : 0;
+  return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pt_last_error(void) { return g_error.c_str(); }
+int pt_abi_version(void) { return PT_ABI_VERSION; }
+
+int pt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int pt_set_num_gpus(int n) {
+  if (n < 1) return fail(PT_ERR_INVALID_ARGUMENT, "pt_set_num_gpus: n must be >= 1");
+  const int have = pt_device_count();
+  if (have == 0) return fail(PT_ERR_NO_DEVICE, "no CUDA device available");
+  if (n > have) return fail(PT_ERR_INVALID_ARGUMENT, "pt_set_num_gpus: more GPUs requested than visible");
+  g_num_gpus = n;
+  return PT_OK;
+}
+int pt_get_num_gpus(void) { return g_num_gpus; }
+
+int pt_get_stats(pt_stats* out) {
+  if (!out) return fail(PT_ERR_INVALID_ARGUMENT, "pt_get_stats: null argument");
+  *out = g_stats;
+  return PT_OK;
+}
+
+int pt_scene_upload(const pt_scene* scene, int device, pt_device_scene** out) {
+  return upload(scene, device, out, nullptr, nullptr);
+}
+
+void pt_scene_free(pt_device_scene* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaFree(s->arena);
+  delete s;
+}
+
+int pt_render_region_device(const pt_device_scene* cscene, int width, int height, int spp, int depth,
+                            const pt_camera* camera, const pt_region* region, float* d_out, int64_t out_row_pitch,
+                            void* stream) {
+  pt_device_scene* scene = const_cast<pt_device_scene*>(cscene);
+  if (!scene) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render_region_device: null scene");
+  const int rc = check_render_args(width, height, spp, camera, region, d_out);
+  if (rc != PT_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PT_CUDA(cudaSetDevice(scene->device));
+  if (region->w == 0 || region->h == 0) return PT_OK;
+  if (depth <= 0) {
+    // render.hpp:58,91: no bounce allowed -> every sample returns black
+    PT_CUDA(cudaMemset2DAsync(d_out, out_row_pitch * sizeof(float), 0, (size_t)region->w * 3 * sizeof(float), region->h, st));
+    return PT_OK;
+  }
+  RenderParams p;
+  p.scene = scene->desc;
+  p.cam = *camera;
+  p.width = width, p.height = height, p.spp = spp, p.depth = depth;
+  p.region = *region;
+  p.out = d_out;
+  p.out_row_pitch = out_row_pitch;
+  const int slot = scene->next_slot;
+  scene->next_slot = (slot + 1) % kCounterSlots;
+  p.pixel_counter = scene->queue_heads + slot;
+  p.counters = scene->counters;
+  PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, sizeof(unsigned long long), st));
+  cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
+  if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
+  scene->paths_launched += (unsigned long long)region->w * region->h * spp;
+  return PT_OK;
+}
+
+int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* scans, int reset) {
+  if (!scene) return fail(PT_ERR_INVALID_ARGUMENT, "pt_scene_read_counters: null scene");
+  PT_CUDA(cudaSetDevice(scene->device));
+  PT_CUDA(cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  PT_CUDA(cudaMemcpy(&v, scene->counters, sizeof v, cudaMemcpyDeviceToHost));
+  if (paths) *paths = scene->paths_launched;
+  if (scans) *scans = v;
+  if (reset) {
+    PT_CUDA(cudaMemset(scene->counters, 0, sizeof(unsigned long long)));
+    scene->paths_launched = 0;
+  }
+  return PT_OK;
+}
+
+// ---- blocking host-buffer path (what render<W,H,S>() of render.hpp:141-160 becomes)
+int pt_render_region(int width, int height, int spp, int depth, const pt_camera* camera, const pt_scene* hitables,
+                     const pt_region* region, float* out, int64_t out_row_pitch) {
+  if (!hitables) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render_region: null scene");
+  int rc = check_render_args(width, height, spp, camera, region, out);
+  if (rc != PT_OK) return rc;
+  pt_stats st {};
+  st.n_gpus = 1;
+  pt_device_scene* ds = nullptr;
+  rc = upload(hitables, 0, &ds, &st.h2d_ms, &st.h2d_bytes);
+  if (rc != PT_OK) return rc;
+  const size_t row_floats = (size_t)region->w * 3;
+  float* d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_out, std::max<size_t>(row_floats * region->h, 1) * sizeof(float));
+  if (e != cudaSuccess) {
+    pt_scene_free(ds);
+    return cuda_fail(e, "cudaMalloc(framebuffer)");
+  }
+  cudaEvent_t ev[4];
+  for (auto& x : ev) cudaEventCreate(&x);
+  cudaEventRecord(ev[0], 0);
+  rc = pt_render_region_device(ds, width, height, spp, depth, camera, region, d_out, (int64_t)row_floats, nullptr);
+  cudaEventRecord(ev[1], 0);
+  if (rc == PT_OK) {
+    cudaEventRecord(ev[2], 0);
+    e = cudaMemcpy2DAsync(out, out_row_pitch * sizeof(float), d_out, row_floats * sizeof(float),
+                          row_floats * sizeof(float), region->h, cudaMemcpyDeviceToHost, 0);
+    cudaEventRecord(ev[3], 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = cuda_fail(e, "framebuffer download");
+  }
+  if (rc == PT_OK) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]);
+    st.kernel_ms = ms;
+    cudaEventElapsedTime(&ms, ev[2], ev[3]);
+    st.d2h_ms = ms;
+    st.d2h_bytes = row_floats * region->h * sizeof(float);
+    st.kernel_launches = depth > 0 ? 1 : 0;
+    uint64_t paths = 0, scans = 0;
+    pt_scene_read_counters(ds, &paths, &scans, 0);
+    st.paths = (uint64_t)region->w * region->h * spp, st.scans = scans;
+    g_stats = st;
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  cudaFree(d_out);
+  pt_scene_free(ds);
+  return rc;
+}
+
+int pt_render(int width, int height, int spp, int depth, const pt_camera* camera, const pt_scene* hitables, float* fb) {
+  if (!hitables || !camera || !fb) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render: null argument");
+  if (width <= 0 || height <= 0 || spp <= 0) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render: width, height and spp must be positive");
+  const int n = g_num_gpus;
+  if (n == 1) {
+    const pt_region full = rows_of(width, height, 0, 1);
+    return pt_render_region(width, height, spp, depth, camera, hitables, &full, fb, (int64_t)width * 3);
+  }
+  // ---- multi-GPU, one process: rows interleaved over the GPUs (row y -> GPU
+  // y mod n); every GPU stores its pixels straight into GPU 0's framebuffer
+  // through peer-mapped memory over NVLink.  Without peer access the rows are
+  // rendered into a local buffer and copied into place afterwards.
+  if (pt_device_count() < n) return fail(PT_ERR_NO_DEVICE, "pt_render: fewer CUDA devices than pt_set_num_gpus()");
+  pt_stats st {};
+  st.n_gpus = (uint32_t)n;
+  std::vector<pt_device_scene*> scenes(n, nullptr);
+  std::vector<float*> local(n, nullptr);
+  std::vector<cudaStream_t> streams(n, nullptr);
+  std::vector<cudaEvent_t> ev0(n), ev1(n);
+  float* fb0 = nullptr;
+  int rc = PT_OK;
+  const size_t row_floats = (size_t)width * 3;
+  auto cleanup = [&]() {
+    for (int d = 0; d < n; ++d) {
+      cudaSetDevice(d);
+      if (local[d]) cudaFree(local[d]);
+      if (streams[d]) cudaStreamDestroy(streams[d]);
+      if (scenes[d]) pt_scene_free(scenes[d]);
+    }
+    cudaSetDevice(0);
+    if (fb0) cudaFree(fb0);
+  };
+  cudaSetDevice(0);
+  cudaError_t e = cudaMalloc(&fb0, row_floats * height * sizeof(float));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(framebuffer)");
+  for (int d = 0; d < n && rc == PT_OK; ++d) {
+    rc = upload(hitables, d, &scenes[d], &st.h2d_ms, &st.h2d_bytes);
+    if (rc != PT_OK) break;
+    cudaSetDevice(d);
+    cudaStreamCreateWithFlags(&streams[d], cudaStreamNonBlocking);
+    cudaEventCreate(&ev0[d]), cudaEventCreate(&ev1[d]);
+  }
+  for (int d = 0; d < n && rc == PT_OK; ++d) {
+    cudaSetDevice(d);
+    const pt_region rg = rows_of(width, height, d, n);
+    float* target = fb0 + (size_t)d * row_floats;
+    int64_t pitch = (int64_t)n * (int64_t)row_floats;
+    if (d != 0) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, d, 0);
+      if (can) {
+        e = cudaDeviceEnablePeerAccess(0, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+        cudaGetLastError();
+      }
+      if (!can) {
+        e = cudaMalloc(&local[d], std::max<size_t>(row_floats * rg.h, 1) * sizeof(float));
+        if (e != cudaSuccess) {
+          rc = cuda_fail(e, "cudaMalloc(local rows)");
+          break;
+        }
+        target = local[d], pitch = (int64_t)row_floats;
+      }
+    }
+    cudaEventRecord(ev0[d], streams[d]);
+    rc = pt_render_region_device(scenes[d], width, height, spp, depth, camera, &rg, target, pitch, streams[d]);
+    cudaEventRecord(ev1[d], streams[d]);
+    if (rc == PT_OK && local[d])
+      cudaMemcpy2DAsync(fb0 + (size_t)d * row_floats, (size_t)n * row_floats * sizeof(float), local[d],
+                        row_floats * sizeof(float), row_floats * sizeof(float), rg.h, cudaMemcpyDefault, streams[d]);
+  }
+  for (int d = 0; d < n && rc == PT_OK; ++d) {
+    cudaSetDevice(d);
+    e = cudaStreamSynchronize(streams[d]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "multi-GPU render");
+    float ms = 0.f;
+    if (rc == PT_OK && cudaEventElapsedTime(&ms, ev0[d], ev1[d]) == cudaSuccess) st.kernel_ms = std::max<double>(st.kernel_ms, ms);
+    uint64_t scans = 0;
+    if (rc == PT_OK && pt_scene_read_counters(scenes[d], nullptr, &scans, 0) == PT_OK) st.scans += scans;
+    cudaEventDestroy(ev0[d]), cudaEventDestroy(ev1[d]);
+  }
+  if (rc == PT_OK) {
+    cudaSetDevice(0);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a), cudaEventCreate(&b);
+    cudaEventRecord(a, 0);
+    e = cudaMemcpyAsync(fb, fb0, row_floats * height * sizeof(float), cudaMemcpyDeviceToHost, 0);
+    cudaEventRecord(b, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) rc = cuda_fail(e, "framebuffer download");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    st.d2h_ms = ms, st.d2h_bytes = row_floats * height * sizeof(float);
+    cudaEventDestroy(a), cudaEventDestroy(b);
+    st.paths = (uint64_t)width * height * spp;
+    st.kernel_launches = depth > 0 ? (uint32_t)n : 0;
+    g_stats = st;
+  }
+  cleanup();
+  return rc;
+}
+
+int render(int width, int height, int spp, int depth, const pt_camera* camera, const pt_scene* hitables, float* fb) {
+  return pt_render(width, height, spp, depth, camera, hitables, fb);
+}
+
+// ---- framebuffer sharing between the one-process-per-GPU ranks --------------
+int pt_fb_alloc(int device, size_t bytes, float** d_ptr) {
+  if (!d_ptr) return fail(PT_ERR_INVALID_ARGUMENT, "pt_fb_alloc: null argument");
+  PT_CUDA(cudaSetDevice(device));
+  PT_CUDA(cudaMalloc(d_ptr, std::max<size_t>(bytes, 16)));
+  return PT_OK;
+}
+int pt_fb_free(int device, float* d_ptr) {
+  PT_CUDA(cudaSetDevice(device));
+  PT_CUDA(cudaFree(d_ptr));
+  return PT_OK;
+}
+int pt_fb_export(float* d_ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  PT_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+  std::memcpy(handle, &h, 64);
+  return PT_OK;
+}
+int pt_fb_open(int device, const unsigned char handle[64], float** d_ptr) {
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  PT_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  PT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *d_ptr = static_cast<float*>(p);
+  return PT_OK;
+}
+int pt_fb_close(float* d_ptr) {
+  PT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return PT_OK;
+}
+
+}  // extern "C"
+
+// ---- FP32 roofline denominator: register-resident FFMA throughput -----------
+namespace {
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+        x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = __fmaf_rn(x0, a, b), x1 = __fmaf_rn(x1, a, b), x2 = __fmaf_rn(x2, a, b), x3 = __fmaf_rn(x3, a, b);
+      x4 = __fmaf_rn(x4, a, b), x5 = __fmaf_rn(x5, a, b), x6 = __fmaf_rn(x6, a, b), x7 = __fmaf_rn(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+}  // namespace
+
+extern "C" int pt_measure_fp32_peak(int device, double* tflops, double* sm_mhz_est) {
+  if (!tflops) return fail(PT_ERR_INVALID_ARGUMENT, "pt_measure_fp32_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PT_ERR_NO_DEVICE, "no CUDA device available");
+  PT_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  PT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int grid = sms * 8, block = 256, iters = 4096;
+  float* d = nullptr;
+  PT_CUDA(cudaMalloc(&d, (size_t)grid * block * sizeof(float)));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a), cudaEventCreate(&b);
+  double best_ms = 1e30;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a, 0);
+    ffma_peak_kernel<<<grid, block>>>(d, iters, 0.999f, 0.001f);
+    cudaEventRecord(b, 0);
+    cudaError_t e = cudaEventSynchronize(b);
+    if (e != cudaSuccess) {
+      cudaFree(d);
+      return cuda_fail(e, "ffma_peak_kernel");
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0) best_ms = std::min<double>(best_ms, ms);
+  }
+  cudaEventDestroy(a), cudaEventDestroy(b);
+  cudaFree(d);
+  const double fmas = (double)grid * block * (double)iters * 16.0 * 8.0;
+  *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+  if (sm_mhz_est) *sm_mhz_est = fmas / (best_ms * 1e-3) / ((double)sms * 128.0) / 1e6;
+  return PT_OK;
+}

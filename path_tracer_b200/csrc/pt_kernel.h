@@ -1,0 +1,43 @@
+// pt_kernel.h -- launch interface of the render kernel (pt_kernel.cu).
+#ifndef PT_KERNEL_H
+#define PT_KERNEL_H
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pt_abi.h"
+#include "pt_packed.h"
+
+namespace ptb {
+
+#ifndef PT_BLOCK_THREADS
+#define PT_BLOCK_THREADS 128
+#endif
+#ifndef PT_MIN_BLOCKS_PER_SM
+#define PT_MIN_BLOCKS_PER_SM 4
+#endif
+constexpr int kBlockThreads = PT_BLOCK_THREADS;
+constexpr int kMinBlocksPerSM = PT_MIN_BLOCKS_PER_SM;
+constexpr int kMaxBlocksPerSM = PT_MIN_BLOCKS_PER_SM;  // persistent grid = SMs x this
+
+struct RenderParams {
+  SceneDesc scene;
+  pt_camera cam;
+  int width, height, spp, depth;
+  pt_region region;
+  float* out;               // device (or peer-mapped) pointer
+  long long out_row_pitch;  // floats
+  unsigned long long* pixel_counter;  // work-queue head, zeroed before launch
+  unsigned long long* counters;       // [0] += closest-hit scans (may be null)
+};
+
+struct LaunchInfo {
+  int grid, block, smem_bytes, blocks_per_sm;
+  bool staged;  // scan blob staged in shared memory (else streamed from L2)
+};
+
+int max_smem_blob_bytes(int device);
+cudaError_t launch_render(const RenderParams& p, int device, int grid_override, cudaStream_t stream,
+                          LaunchInfo* info);
+
+}  // namespace ptb
+#endif

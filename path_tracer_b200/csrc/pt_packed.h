@@ -1,0 +1,120 @@
+// pt_packed.h -- device-side scene layout, shared by the host packer
+// (pt_pack.cpp) and the kernels (pt_kernel.cu).
+//
+// The reference keeps the scene as an array of 624-byte std::variant objects
+// and walks it sequentially per ray (render.hpp:30-51).  Here the variant list
+// becomes
+//   * a "scan blob": float4-packed, per-kind structure-of-arrays holding ONLY
+//     what the closest-hit scan needs, ordered as a list of GROUPS.  The blob
+//     is staged into shared memory once per CTA (cp.async.bulk) and every warp
+//     streams it with broadcast LDS.128;
+//   * small per-object side tables in global memory (material, original index
+//     key, radius, normals) that are touched once per accepted hit.
+//
+// Groups: objects are re-ordered by kind inside SEGMENTS delimited by
+// constant_medium objects (the only primitive whose result depends on the
+// running closest-t and which draws RNG, constant_medium.hpp:52-65).  Within a
+// segment the winner is picked by (minimum t, then maximum KEY), which
+// reproduces the sequential scan's tie behaviour exactly for any visiting
+// order (DESIGN.md "closest-hit order semantics"):
+//   key = -1 - original_index   for spheres  (earlier sphere keeps a tie,
+//                                             sphere.hpp:77,93 use strict <)
+//   key = original_index        otherwise    (later object takes a tie,
+//                                             rectangle.hpp:36, triangle.hpp:91)
+#ifndef PT_PACKED_H
+#define PT_PACKED_H
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PT_HD __host__ __device__
+#else
+#define PT_HD
+#endif
+
+namespace ptb {
+
+enum GroupType : int {
+  G_SPHERE = 0,         // static spheres: 1 float4 {cx, cy, cz, r*r}
+  G_MOVING_SPHERE = 1,  // 2 float4 {c0x, c0y, c0z, r*r} {c1x-c0x, c1y-c0y, c1z-c0z, 0}; one (time0,time1) class
+  G_RECT = 2,           // 2 float4 {a0, a1, b0, b1} {k, axis, 0, 0}
+  G_TRIANGLE = 3,       // 3 float4 {v0, 0} {v1-v0, 0} {v2-v0, 0}
+  G_BOX = 4,            // 2 float4 {p0, 0} {p1, 0}
+  G_MEDIUM = 5          // `begin` = index into the media table; closes a segment
+};
+
+constexpr int kSphereChunk = 32;  // static / moving sphere groups are padded to this many
+
+struct Group {  // 32 bytes
+  int32_t type;
+  int32_t begin;  // first element, in elements of this kind's array
+  int32_t count;  // padded count for sphere groups
+  float time0;    // G_MOVING_SPHERE: the class's time0
+  float den;      // G_MOVING_SPHERE: time1 - time0 (sphere.hpp:55)
+  int32_t pad[3];
+};
+
+// Unified object id carried by the scan: kind in the top bits.
+constexpr int kIdShift = 27;
+constexpr uint32_t kIdMask = (1u << kIdShift) - 1u;
+PT_HD inline int make_id(int type, int index) { return (type << kIdShift) | index; }
+
+struct SphereAux {  // 32 bytes; index = element index in the static / moving array
+  float radius;     // sphere.hpp:81 divides by it
+  float time0, den; // moving only
+  int32_t material;
+  int32_t key;
+  int32_t pad[3];
+};
+
+struct ObjAux {  // 8 bytes: rects, boxes
+  int32_t material;
+  int32_t key;
+};
+
+struct TriAux {  // 32 bytes
+  float nx, ny, nz;  // cross(edge1, edge2), unnormalised (triangle.hpp:96)
+  int32_t material;
+  int32_t key;
+  int32_t pad[3];
+};
+
+struct MediumRec {  // constant_medium.hpp:80-82 with its boundary inlined
+  int32_t boundary_kind;
+  float neg_inv_density;  // -1 / density (constant_medium.hpp:20)
+  int32_t material;
+  int32_t key;
+  // sphere boundary (sphere.hpp:108-113)
+  float c0[3];
+  float dv[3];  // center1 - center0
+  float radius, r2, time0, den;
+  int32_t moving;
+  // box boundary (box.hpp:20-25)
+  float p0[3];
+  float p1[3];
+  int32_t pad;
+};
+
+// Everything the kernel needs to find its data; passed by value as a kernel
+// parameter.  Blob offsets are in BYTES from the blob start, 16-byte aligned.
+struct SceneDesc {
+  const unsigned char* blob;  // global copy of the scan blob
+  uint32_t blob_bytes;        // multiple of 16
+  uint32_t n_groups;
+  uint32_t off_groups, off_sphere, off_moving, off_rect, off_triangle, off_box;
+  uint32_t n_objects;         // reference n_hittables (for work accounting)
+  const SphereAux* sphere_aux;
+  const SphereAux* moving_aux;
+  const ObjAux* rect_aux;
+  const TriAux* tri_aux;
+  const ObjAux* box_aux;
+  const MediumRec* media;
+  const void* materials;  // pt_material[]
+  const void* textures;   // pt_texture[]
+  const unsigned char* texture_bytes;
+  uint64_t n_texture_texels;
+  uint32_t n_materials, n_textures;
+};
+
+}  // namespace ptb
+#endif
