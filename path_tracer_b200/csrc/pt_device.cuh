@@ -58,17 +58,22 @@ PT_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {
 }
 
 // ---- transcendentals: binary64 evaluation, one rounding to binary32 -------
-PT_DEV float t_sin(float x) { return __double2float_rn(sin((double)x)); }
+__device__ __noinline__ float t_sin(float x) { return __double2float_rn(sin((double)x)); }
 PT_DEV float t_cos(float x) { return __double2float_rn(cos((double)x)); }
-PT_DEV void t_sincos(float x, float& s, float& c) {
+// Out-of-line (one copy in the kernel image; the scan loop must own the instruction
+// cache) and by value (nothing forced into local memory).
+__device__ __noinline__ float2 t_sincos2(float x) {
   double ds, dc;
   sincos((double)x, &ds, &dc);
-  s = __double2float_rn(ds);
-  c = __double2float_rn(dc);
+  return make_float2(__double2float_rn(ds), __double2float_rn(dc));
+}
+PT_DEV void t_sincos(float x, float& s, float& c) {
+  const float2 r = t_sincos2(x);
+  s = r.x, c = r.y;
 }
 PT_DEV float t_asin(float x) { return __double2float_rn(asin((double)x)); }
 PT_DEV float t_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
-PT_DEV float t_log(float x) { return __double2float_rn(log((double)x)); }
+__device__ __noinline__ float t_log(float x) { return __double2float_rn(log((double)x)); }
 // pow(x, 5.0f) (material.hpp:65): x^5 by binary64 products (4 roundings at 2^-53)
 PT_DEV float t_pow5(float x) {
   const double d = (double)x;

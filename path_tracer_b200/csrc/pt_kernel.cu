@@ -35,6 +35,10 @@ namespace ptb {
 namespace {
 
 constexpr float kTMin = 0.001f;  // render.hpp:40
+#ifndef PT_SCAN_UNROLL
+#define PT_SCAN_UNROLL 4
+#endif
+constexpr int kScanUnroll = PT_SCAN_UNROLL;  // spheres per hot-loop trip
 
 // ---------------------------------------------------------------- staging
 PT_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -273,17 +277,25 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
     const Group g = sv.groups[gi];
     switch (g.type) {
       case G_SPHERE: {
+#pragma unroll 1
         for (int base = g.begin; base < g.begin + g.count; base += kSphereChunk) {
           const float4* __restrict__ p = sv.sphere + base;
           uint32_t mask = 0;
+          // Branch-free discriminant pass; kScanUnroll spheres per loop trip keeps
+          // the hot loop inside the instruction cache (DESIGN.md "scan loop").
+#pragma unroll 1
+          for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
+            uint32_t nib = 0;
 #pragma unroll
-          for (int j = 0; j < kSphereChunk; ++j) {
-            const float4 s = ld4<kSmem>(p + j);
-            const float ocx = fsub(r.o.x, s.x), ocy = fsub(r.o.y, s.y), ocz = fsub(r.o.z, s.z);
-            const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-            const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), s.w);
-            const float disc = fsub(fmul(b, b), fmul(a, c));
-            if (disc > 0.f) mask |= (1u << j);
+            for (int j = 0; j < kScanUnroll; ++j) {
+              const float4 s = ld4<kSmem>(p + it + j);
+              const float ocx = fsub(r.o.x, s.x), ocy = fsub(r.o.y, s.y), ocz = fsub(r.o.z, s.z);
+              const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
+              const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), s.w);
+              const float disc = fsub(fmul(b, b), fmul(a, c));
+              if (disc > 0.f) nib |= (1u << j);
+            }
+            mask |= nib << it;
           }
           if (!live) mask = 0;
           while (mask) {
@@ -297,19 +309,25 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       }
       case G_MOVING_SPHERE: {
         const float f = fdiv(fsub(r.tm, g.time0), g.den);  // sphere.hpp:55
+#pragma unroll 1
         for (int base = g.begin; base < g.begin + g.count; base += kSphereChunk) {
           const float4* __restrict__ p = sv.moving + 2 * base;
           uint32_t mask = 0;
+#pragma unroll 1
+          for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
+            uint32_t nib = 0;
 #pragma unroll
-          for (int j = 0; j < kSphereChunk; ++j) {
-            const float4 s = ld4<kSmem>(p + 2 * j);
-            const float4 v = ld4<kSmem>(p + 2 * j + 1);
-            const float cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z));
-            const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
-            const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-            const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), s.w);
-            const float disc = fsub(fmul(b, b), fmul(a, c));
-            if (disc > 0.f) mask |= (1u << j);
+            for (int j = 0; j < kScanUnroll; ++j) {
+              const float4 s = ld4<kSmem>(p + 2 * (it + j));
+              const float4 v = ld4<kSmem>(p + 2 * (it + j) + 1);
+              const float cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z));
+              const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
+              const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
+              const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), s.w);
+              const float disc = fsub(fmul(b, b), fmul(a, c));
+              if (disc > 0.f) nib |= (1u << j);
+            }
+            mask |= nib << it;
           }
           if (!live) mask = 0;
           while (mask) {

@@ -16,7 +16,8 @@ import numpy as np
 from . import abi
 from .scene import camera_c
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libptb200.so")
+LIB_PATH = os.environ.get("PTB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                        "libptb200.so")
 
 
 class PathTracerError(RuntimeError):
