@@ -40,6 +40,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kCounterSlots = 64;
+constexpr int kCounterWords = 8;  // [0] scans, [1] first CTA start (ns), [2] queue ran dry (ns), [3] last warp retired (ns)
 
 }  // namespace
 
@@ -90,10 +91,25 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   const size_t o_taux = place(host, ps.tri_aux);
   const size_t o_baux = place(host, ps.box_aux);
   const size_t o_media = place(host, ps.media);
+  std::vector<int32_t> keys;
+  uint32_t key_base[6];
+  key_base[G_SPHERE] = (uint32_t)keys.size();
+  for (const auto& a : ps.sphere_aux) keys.push_back(a.key);
+  key_base[G_MOVING_SPHERE] = (uint32_t)keys.size();
+  for (const auto& a : ps.moving_aux) keys.push_back(a.key);
+  key_base[G_RECT] = (uint32_t)keys.size();
+  for (const auto& a : ps.rect_aux) keys.push_back(a.key);
+  key_base[G_TRIANGLE] = (uint32_t)keys.size();
+  for (const auto& a : ps.tri_aux) keys.push_back(a.key);
+  key_base[G_BOX] = (uint32_t)keys.size();
+  for (const auto& a : ps.box_aux) keys.push_back(a.key);
+  key_base[G_MEDIUM] = (uint32_t)keys.size();
+  for (const auto& a : ps.media) keys.push_back(a.key);
+  const size_t o_keys = place(host, keys);
   const size_t o_mat = place(host, ps.materials);
   const size_t o_tex = place(host, ps.textures);
   const size_t o_heads = align_up(host.size(), 256);
-  host.resize(o_heads + sizeof(unsigned long long) * (kCounterSlots + 2), 0);
+  host.resize(o_heads + sizeof(unsigned long long) * (kCounterSlots + kCounterWords), 0);
   const size_t o_bytes = align_up(host.size(), 256);
   const size_t tex_bytes = std::max<size_t>((size_t)scene->n_texture_bytes, 3);
   const size_t total = o_bytes + align_up(tex_bytes, 256);
@@ -141,6 +157,8 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   d.tri_aux = reinterpret_cast<const TriAux*>(ds->arena + o_taux);
   d.box_aux = reinterpret_cast<const ObjAux*>(ds->arena + o_baux);
   d.media = reinterpret_cast<const MediumRec*>(ds->arena + o_media);
+  d.keys = reinterpret_cast<const int32_t*>(ds->arena + o_keys);
+  for (int k = 0; k < 6; ++k) d.key_base[k] = key_base[k];
   d.materials = ds->arena + o_mat;
   d.textures = ds->arena + o_tex;
   d.texture_bytes = ds->arena + o_bytes;
@@ -237,6 +255,8 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   p.pixel_counter = scene->queue_heads + slot;
   p.counters = scene->counters;
   PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 1, 0xff, 2 * sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 3, 0, sizeof(unsigned long long), st));
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
   scene->paths_launched += (unsigned long long)region->w * region->h * spp;
@@ -255,6 +275,17 @@ int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* sc
     PT_CUDA(cudaMemset(scene->counters, 0, sizeof(unsigned long long)));
     scene->paths_launched = 0;
   }
+  return PT_OK;
+}
+
+// Debug aid (not part of pt_abi.h): timeline of the LAST launch on this scene, in ns:
+// out[0] = queue-dry - start, out[1] = last-warp-retired - start.
+int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[2]) {
+  PT_CUDA(cudaSetDevice(scene->device));
+  PT_CUDA(cudaDeviceSynchronize());
+  unsigned long long v[4];
+  PT_CUDA(cudaMemcpy(v, scene->counters, sizeof v, cudaMemcpyDeviceToHost));
+  out[0] = v[2] - v[1], out[1] = v[3] - v[1];
   return PT_OK;
 }
 

@@ -24,8 +24,11 @@ namespace ptb {
 PT_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
 PT_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
 PT_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
-PT_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-PT_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
+// IEEE division and square root expand to ~30 / ~15 instructions each; they are never in the scan
+// loop, so ONE out-of-line copy keeps the kernel's instruction footprint small (the scan loop must
+// own the instruction cache, see DESIGN.md "instruction cache").
+__device__ __noinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __noinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
 
 struct V3 {
   float x, y, z;

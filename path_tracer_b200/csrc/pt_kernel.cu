@@ -39,6 +39,29 @@ constexpr float kTMin = 0.001f;  // render.hpp:40
 #define PT_SCAN_UNROLL 4
 #endif
 constexpr int kScanUnroll = PT_SCAN_UNROLL;  // spheres per hot-loop trip
+#ifndef PT_BOOST_ROUNDS
+#define PT_BOOST_ROUNDS 0
+#endif
+#ifndef PT_HEAVY_PER_SAMPLE
+#define PT_HEAVY_PER_SAMPLE 8
+#endif
+constexpr int kBoostRounds = PT_BOOST_ROUNDS;        // short rounds for heavy pixels between two normal rounds
+constexpr int kHeavyPerSample = PT_HEAVY_PER_SAMPLE;  // a pixel is heavy above this many scans per sample ...
+constexpr int kHeavyBase = 32;                        // ... plus this head start
+#ifndef PT_RAMP_BETA
+#define PT_RAMP_BETA 0.0f
+#endif
+constexpr float kRampBeta = PT_RAMP_BETA;  // ramp-down starts when remaining pixels < 32 * warps * beta
+#ifndef PT_TEAM_MAX_LIVE
+#define PT_TEAM_MAX_LIVE 16
+#endif
+constexpr int kTeamMaxLive = PT_TEAM_MAX_LIVE;  // at or below this many live lanes the warp scans in teams
+
+PT_DEV unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 // ---------------------------------------------------------------- staging
 PT_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,16 +118,7 @@ struct Best {
 };
 
 PT_DEV int key_of(const SceneDesc& sc, int id) {
-  const int type = id >> kIdShift;
-  const int idx = id & (int)kIdMask;
-  switch (type) {
-    case G_SPHERE: return sc.sphere_aux[idx].key;
-    case G_MOVING_SPHERE: return sc.moving_aux[idx].key;
-    case G_RECT: return sc.rect_aux[idx].key;
-    case G_TRIANGLE: return sc.tri_aux[idx].key;
-    case G_BOX: return sc.box_aux[idx].key;
-    default: return sc.media[idx].key;
-  }
+  return sc.keys[sc.key_base[id >> kIdShift] + (uint32_t)(id & (int)kIdMask)];
 }
 
 // Winner rule: minimum t, then maximum key (pt_packed.h).  Called with a
@@ -194,24 +208,28 @@ PT_DEV bool rect_hit_t(const Ray& r, int axis, float a0, float a1, float b0, flo
   return true;
 }
 
-// box.hpp:29-50 over the six sides of box.hpp:20-25.  Returns the winning side.
+// box.hpp:29-50 over the six sides of box.hpp:20-25 (xy@p1.z, xy@p0.z, xz@p1.y, xz@p0.y, yz@p1.x,
+// yz@p0.x; a later side takes a tie).  Returns the winning side or -1.  One loop body instead of six
+// inlined rectangles keeps the code small.
 PT_DEV int box_hit_t(const Ray& r, V3 p0, V3 p1, float tmin, float tmax, float& t_out, float& a_out,
                      float& b_out) {
   int side = -1;
   float closest = tmax;
-  float t, a, b;
-  if (rect_hit_t(r, PT_AXIS_XY, p0.x, p1.x, p0.y, p1.y, p1.z, tmin, closest, t, a, b))
-    side = 0, closest = t, t_out = t, a_out = a, b_out = b;
-  if (rect_hit_t(r, PT_AXIS_XY, p0.x, p1.x, p0.y, p1.y, p0.z, tmin, closest, t, a, b))
-    side = 1, closest = t, t_out = t, a_out = a, b_out = b;
-  if (rect_hit_t(r, PT_AXIS_XZ, p0.x, p1.x, p0.z, p1.z, p1.y, tmin, closest, t, a, b))
-    side = 2, closest = t, t_out = t, a_out = a, b_out = b;
-  if (rect_hit_t(r, PT_AXIS_XZ, p0.x, p1.x, p0.z, p1.z, p0.y, tmin, closest, t, a, b))
-    side = 3, closest = t, t_out = t, a_out = a, b_out = b;
-  if (rect_hit_t(r, PT_AXIS_YZ, p0.y, p1.y, p0.z, p1.z, p1.x, tmin, closest, t, a, b))
-    side = 4, closest = t, t_out = t, a_out = a, b_out = b;
-  if (rect_hit_t(r, PT_AXIS_YZ, p0.y, p1.y, p0.z, p1.z, p0.x, tmin, closest, t, a, b))
-    side = 5, closest = t, t_out = t, a_out = a, b_out = b;
+#pragma unroll 1
+  for (int s = 0; s < 6; ++s) {
+    const int axis = s >> 1;  // PT_AXIS_XY, PT_AXIS_XZ, PT_AXIS_YZ
+    const bool hi = (s & 1) == 0;
+    float a0, a1, b0, b1, k;
+    if (axis == PT_AXIS_XY)
+      a0 = p0.x, a1 = p1.x, b0 = p0.y, b1 = p1.y, k = hi ? p1.z : p0.z;
+    else if (axis == PT_AXIS_XZ)
+      a0 = p0.x, a1 = p1.x, b0 = p0.z, b1 = p1.z, k = hi ? p1.y : p0.y;
+    else
+      a0 = p0.y, a1 = p1.y, b0 = p0.z, b1 = p1.z, k = hi ? p1.x : p0.x;
+    float t, a, b;
+    if (rect_hit_t(r, axis, a0, a1, b0, b1, k, tmin, closest, t, a, b))
+      side = s, closest = t, t_out = t, a_out = a, b_out = b;
+  }
   return side;
 }
 
@@ -387,6 +405,135 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
   return best;
 }
 
+
+// ---------------------------------------------------------------- team scan (tail mode)
+// When only k < 32 lanes of a warp still own a pixel (the work queue has run
+// dry), one ray per lane would leave most of the warp idle and -- worse --
+// leave the deepest paths of the image on a serial critical path.  The warp
+// is then split into teams of T = 32 / pow2ceil(k) lanes, one team per live
+// ray: member m of a team tests objects m, m+T, ... exactly, and the members'
+// winners are merged with the same (minimum t, maximum key) rule, so the
+// result is bit-identical to the per-lane scan for any T.  A constant_medium
+// still sees the running closest hit of ALL lower-index objects: the team
+// merges before evaluating it, and every member replays its RNG draw on a copy
+// of the owner's generator.
+struct KeyedBest {
+  float t;
+  int id;
+  int key;
+};
+
+PT_DEV void offer(KeyedBest& m, float t, int id, int key) {
+  if (t < m.t || (t == m.t && key > m.key) || m.id < 0) m.t = t, m.id = id, m.key = key;
+}
+// rect / triangle / box let NaN through their range test (rectangle.hpp:36)
+PT_DEV void offer_le(KeyedBest& m, float t, int id, int key) {
+  if (!(t == m.t) || key > m.key || m.id < 0) m.t = t, m.id = id, m.key = key;
+}
+
+PT_DEV void team_merge(KeyedBest& m, int team_size) {
+  for (int o = team_size >> 1; o > 0; o >>= 1) {
+    const float ot = __shfl_xor_sync(0xffffffffu, m.t, o);
+    const int oid = __shfl_xor_sync(0xffffffffu, m.id, o);
+    const int okey = __shfl_xor_sync(0xffffffffu, m.key, o);
+    if (oid >= 0 && (m.id < 0 || ot < m.t || (ot == m.t && okey > m.key))) m.t = ot, m.id = oid, m.key = okey;
+  }
+}
+
+PT_DEV void team_sphere(KeyedBest& m, const Ray& r, float a, float cx, float cy, float cz, float r2, int id,
+                        const SphereAux* aux) {
+  const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
+  const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
+  const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
+  const float disc = fsub(fmul(b, b), fmul(a, c));
+  if (!(disc > 0.f) || (b > 0.f && c > 0.f)) return;
+  const float sq = fsqrt(disc);
+  const float t0 = fdiv(fsub(-b, sq), a);
+  if (t0 < kInf && t0 > kTMin) {
+    if (t0 <= m.t || m.id < 0) offer(m, t0, id, aux->key);
+    return;
+  }
+  const float t1 = fdiv(fadd(-b, sq), a);
+  if (t1 < kInf && t1 > kTMin && (t1 <= m.t || m.id < 0)) offer(m, t1, id, aux->key);
+}
+
+// `member` in [0, team_size); `active` = this team carries a live ray.
+template <bool kSmem>
+PT_DEV Best team_closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, int member,
+                             int team_size, bool active) {
+  KeyedBest m { kInf, -1, 0 };
+  const float a = vdot(r.d, r.d);
+  const int n_groups = (int)sc.n_groups;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const Group g = sv.groups[gi];
+    const int end = active ? g.begin + g.count : 0;
+    switch (g.type) {
+      case G_SPHERE: {
+#pragma unroll 1
+        for (int i = g.begin + member; i < end; i += team_size) {
+          const float4 s = ld4<kSmem>(sv.sphere + i);
+          team_sphere(m, r, a, s.x, s.y, s.z, s.w, make_id(G_SPHERE, i), sc.sphere_aux + i);
+        }
+        break;
+      }
+      case G_MOVING_SPHERE: {
+        const float f = fdiv(fsub(r.tm, g.time0), g.den);
+#pragma unroll 1
+        for (int i = g.begin + member; i < end; i += team_size) {
+          const float4 s = ld4<kSmem>(sv.moving + 2 * i);
+          const float4 v = ld4<kSmem>(sv.moving + 2 * i + 1);
+          const float cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z));
+          team_sphere(m, r, a, cx, cy, cz, s.w, make_id(G_MOVING_SPHERE, i), sc.moving_aux + i);
+        }
+        break;
+      }
+      case G_RECT: {
+#pragma unroll 1
+        for (int i = g.begin + member; i < end; i += team_size) {
+          const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
+          const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
+          float t, ra, rb;
+          if (rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, m.t, t, ra, rb))
+            offer_le(m, t, make_id(G_RECT, i), sc.rect_aux[i].key);
+        }
+        break;
+      }
+      case G_TRIANGLE: {
+#pragma unroll 1
+        for (int i = g.begin + member; i < end; i += team_size) {
+          const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
+          const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
+          const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
+          float t;
+          if (triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, m.t, t))
+            offer_le(m, t, make_id(G_TRIANGLE, i), sc.tri_aux[i].key);
+        }
+        break;
+      }
+      case G_BOX: {
+#pragma unroll 1
+        for (int i = g.begin + member; i < end; i += team_size) {
+          const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
+          const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
+          float t, ra, rb;
+          if (box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, m.t, t, ra, rb) >= 0)
+            offer_le(m, t, make_id(G_BOX, i), sc.box_aux[i].key);
+        }
+        break;
+      }
+      default: {
+        team_merge(m, team_size);  // every member now holds the running closest hit of all lower-index objects
+        float t;
+        if (active && medium_hit_t(sc.media[g.begin], r, kTMin, m.id < 0 ? kInf : m.t, rng, t))
+          m.t = t, m.id = make_id(G_MEDIUM, g.begin), m.key = sc.media[g.begin].key;
+        break;
+      }
+    }
+  }
+  team_merge(m, team_size);
+  return Best { m.id < 0 ? kInf : m.t, m.id };
+}
+
 // ---------------------------------------------------------------- shading
 struct HitRec {  // hitable.hpp:8-18
   V3 p, normal;
@@ -554,6 +701,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
   sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
 
+  if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   const pt_camera& cam = p.cam;
   const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
   const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
@@ -570,35 +718,72 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   V3 att = v3(1.f, 1.f, 1.f);
   V3 acc = v3(0.f, 0.f, 0.f);
   unsigned int n_scans = 0;
+  unsigned int pix_scans = 0;  // closest-hit scans spent on the current pixel
   bool exhausted_queue = false;
+  int warp_cap = 32;  // pixels this warp may hold (ramp-down at the end of the queue)
+  const unsigned long long ramp_div =
+      max(1ull, (unsigned long long)((float)(gridDim.x * (blockDim.x >> 5)) * kRampBeta));
 
-  for (;;) {
+  for (unsigned iter = 0;; ++iter) {
+    // Boost rounds: the image's deepest pixels (paths bouncing dozens of times inside glass) hold
+    // ten times the average work and, one bounce per full-cost round, would sit on a serial
+    // critical path longer than the whole frame.  Between two normal rounds the warp therefore
+    // runs kBoostRounds short rounds for its HEAVY pixels only, scanned by lane teams.
+    const bool boost = (iter % (unsigned)(kBoostRounds + 1)) != 0u;
+    const bool heavy = live && pix_scans > (unsigned)(kHeavyBase + kHeavyPerSample * sample);
+    if (boost && !__any_sync(0xffffffffu, heavy)) continue;
+    const bool part = !boost || heavy;  // this lane takes part in this round
+
     // ---- (A) path regeneration: render.hpp:94-105 sample loop, :130-133 seeding
-    if (need_path && !exhausted_queue) {
-      if (sample == p.spp) {
-        if (live) {
-          // final_color /= samples; fb[y][x] = final_color (render.hpp:102-105)
-          const V3 fin = vdivs(acc, fspp);
-          out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
-          live = false;
+    // A pixel is finished when its last sample ended: write it out (render.hpp:102-105).
+    if (need_path && live && part && sample == p.spp) {
+      const V3 fin = vdivs(acc, fspp);
+      out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+      live = false;
+    }
+    // Pixel fetch with ramp-down: while plenty of pixels remain every lane holds one (cap 32).
+    // Towards the end of the queue a warp may only hold `cap` pixels, cap halving as the queue
+    // drains, so that the pixels still in flight are scanned by ever larger lane teams (shorter
+    // per-pixel latency) instead of leaving a long tail of nearly idle warps.
+    {
+      const bool wants = need_path && !live && !exhausted_queue && !boost;
+      const unsigned want_mask = __ballot_sync(0xffffffffu, wants);
+      if (want_mask != 0u) {
+        const unsigned busy_mask = __ballot_sync(0xffffffffu, live);
+        const int room = warp_cap - __popc(busy_mask);
+        const int my_rank = __popc(want_mask & ((1u << (threadIdx.x & 31u)) - 1u));
+        unsigned fetched_pos = 0u;
+        if (wants && my_rank < room) {
+          const unsigned long long idx = atomicAdd(p.pixel_counter, 1ull);
+          if (idx < n_pixels) {
+            const int k = (int)(idx / (unsigned long long)p.region.w);
+            const int xx = (int)(idx - (unsigned long long)k * (unsigned long long)p.region.w);
+            px = p.region.x0 + xx;
+            py = p.region.y0 + k * p.region.y_stride;
+            out_px = p.out + (long long)k * p.out_row_pitch + 3ll * xx;
+            // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+            rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+            acc = v3(0.f, 0.f, 0.f);
+            sample = 0;
+            pix_scans = 0u;
+            live = true;
+            fetched_pos = (unsigned)min(idx + 1ull, 0xffffffffull);
+          } else {
+            exhausted_queue = true;
+            fetched_pos = 0xffffffffu;
+            if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+          }
         }
-        const unsigned long long idx = atomicAdd(p.pixel_counter, 1ull);
-        if (idx < n_pixels) {
-          const int k = (int)(idx / (unsigned long long)p.region.w);
-          const int xx = (int)(idx - (unsigned long long)k * (unsigned long long)p.region.w);
-          px = p.region.x0 + xx;
-          py = p.region.y0 + k * p.region.y_stride;
-          out_px = p.out + (long long)k * p.out_row_pitch + 3ll * xx;
-          // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
-          rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
-          acc = v3(0.f, 0.f, 0.f);
-          sample = 0;
-          live = true;
-        } else {
-          exhausted_queue = true;
+        const unsigned seen = __reduce_max_sync(0xffffffffu, fetched_pos);
+        if (seen != 0u) {
+          const unsigned long long remaining = seen >= n_pixels ? 0ull : n_pixels - seen;
+          // pixels a warp may hold = remaining pixels per warp (scaled), rounded down to a power of two
+          const unsigned long long per_warp = remaining / ramp_div;
+          warp_cap = per_warp >= 32ull ? 32 : (per_warp <= 1ull ? 1 : (1 << (31 - __clz((int)per_warp))));
         }
       }
-      if (live) {
+    }
+    if (need_path && live && part) {
         // render.hpp:96-99 + camera.hpp:93-100
         const float u = fdiv(fadd((float)px, rng_float(rng)), fwidth);
         const float v = fdiv(fadd((float)py, rng_float(rng)), fheight);
@@ -618,16 +803,45 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
         att = v3(1.f, 1.f, 1.f);
         bounce = 0;
         need_path = false;
-      }
     }
-    if (__all_sync(0xffffffffu, !live)) break;
+    if (!boost && !__any_sync(0xffffffffu, live)) break;
+    const bool act = live && part;
+    const unsigned live_mask = __ballot_sync(0xffffffffu, act);  // lanes with a ray to trace this round
+    if (live_mask == 0u) continue;
 
     // ---- (B) closest hit: render.hpp:60 -> :30-51
-    const Best best = closest_hit<kSmem>(sc, sv, ray, rng, live);
+    Best best { kInf, -1 };
+    const int n_live = __popc(live_mask);
+    if (n_live <= kTeamMaxLive) {
+      // few rays: one TEAM of lanes per ray (see team_closest_hit)
+      const int lane = (int)(threadIdx.x & 31u);
+      int team_size = 32;
+      while (team_size * n_live > 32) team_size >>= 1;  // largest power of two with team_size * n_live <= 32
+      const int team = lane / team_size;
+      const bool active = team < n_live;
+      const int owner = active ? (int)__fns(live_mask, 0u, team + 1) : 0;  // lane of the team-th live ray
+      Ray rr;
+      rr.o.x = __shfl_sync(0xffffffffu, ray.o.x, owner), rr.o.y = __shfl_sync(0xffffffffu, ray.o.y, owner);
+      rr.o.z = __shfl_sync(0xffffffffu, ray.o.z, owner), rr.d.x = __shfl_sync(0xffffffffu, ray.d.x, owner);
+      rr.d.y = __shfl_sync(0xffffffffu, ray.d.y, owner), rr.d.z = __shfl_sync(0xffffffffu, ray.d.z, owner);
+      rr.tm = __shfl_sync(0xffffffffu, ray.tm, owner);
+      Rng rg { __shfl_sync(0xffffffffu, rng.s, owner) };
+      const Best b = team_closest_hit<kSmem>(sc, sv, rr, rg, lane % team_size, team_size, active);
+      // hand the result back: the j-th live lane reads from the first lane of team j
+      const int my_team = __popc(live_mask & ((1u << lane) - 1u));
+      const int src = act ? my_team * team_size : 0;
+      const float bt = __shfl_sync(0xffffffffu, b.t, src);
+      const int bid = __shfl_sync(0xffffffffu, b.id, src);
+      const uint32_t brs = __shfl_sync(0xffffffffu, rg.s, src);
+      if (act) best.t = bt, best.id = bid, rng.s = brs;
+    } else {
+      best = closest_hit<kSmem>(sc, sv, ray, rng, act);
+    }
 
     // ---- (C) shade: render.hpp:58-91
-    if (live) {
+    if (act) {
       ++n_scans;
+      ++pix_scans;
       V3 contribution = v3(0.f, 0.f, 0.f);
       bool path_done = false;
       if (best.id < 0) {
@@ -692,6 +906,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
     }
   }
 
+  if (p.counters && (threadIdx.x & 31) == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   // work counters: one atomic per warp
   unsigned int warp_scans = n_scans;
 #pragma unroll

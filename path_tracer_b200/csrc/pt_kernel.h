@@ -13,7 +13,7 @@ namespace ptb {
 #define PT_BLOCK_THREADS 128
 #endif
 #ifndef PT_MIN_BLOCKS_PER_SM
-#define PT_MIN_BLOCKS_PER_SM 4
+#define PT_MIN_BLOCKS_PER_SM 5
 #endif
 constexpr int kBlockThreads = PT_BLOCK_THREADS;
 constexpr int kMinBlocksPerSM = PT_MIN_BLOCKS_PER_SM;

@@ -109,6 +109,8 @@ struct SceneDesc {
   const TriAux* tri_aux;
   const ObjAux* box_aux;
   const MediumRec* media;
+  const int32_t* keys;    // tie-break keys of every object: keys[key_base[type] + index]
+  uint32_t key_base[6];
   const void* materials;  // pt_material[]
   const void* textures;   // pt_texture[]
   const unsigned char* texture_bytes;

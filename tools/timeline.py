@@ -1,0 +1,16 @@
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch, scenes
+from path_tracer_b200 import render as R
+spp = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+sc, cam, (w, h, _, d) = scenes.load_c1()
+ds = R.DeviceScene(sc, 0)
+fb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
+L = R.lib()
+for i in range(3):
+    ds.render_region(cam, w, h, spp, d, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3, 0)
+    out = (C.c_ulonglong * 2)()
+    L.pt_debug_timeline(ds._h, out)
+    print("spp %d: queue dry at %.2f ms, done at %.2f ms -> tail %.1f%%; steady-state rate %.1f Mpaths/s" % (
+        spp, out[0] / 1e6, out[1] / 1e6, 100 * (out[1] - out[0]) / out[1], w * h * spp / (out[1] / 1e3)))
