@@ -12,7 +12,7 @@ NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
 SRCS := $(CSRC)/pt_kernel.cu $(CSRC)/pt_api.cu $(CSRC)/pt_pack.cpp
 HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/pt_abi.h
 
-all: lib oracle
+all: lib oracle host
 
 lib: $(LIB)
 
@@ -23,7 +23,24 @@ $(LIB): $(SRCS) $(HDRS)
 oracle:
 	$(MAKE) -C oracle
 
+# Host side: the reference's UNMODIFIED application (src/main.cpp, compiled in place) on top of the
+# C++ host mirror in path_tracer_b200/include + compat and libptb200.so.  Only where the reference
+# tree exists; the binary travels to the GPU box.
+REFERENCE ?= /root/reference
+HOST_HDRS := $(wildcard path_tracer_b200/include/pt/*.hpp path_tracer_b200/compat/*.hpp path_tracer_b200/compat/*/*.h*) include/ptscene_io.hpp
+ifneq ($(wildcard $(REFERENCE)/src/main.cpp),)
+host: build/sycl-rt-b200
+build/sycl-rt-b200: $(REFERENCE)/src/main.cpp $(HOST_HDRS) $(LIB)
+	mkdir -p build
+	g++ -std=c++20 -O2 -ffp-contract=off -w -DOUTPUT_WIDTH=800 -DOUTPUT_HEIGHT=480 \
+	    -Ipath_tracer_b200/compat -Ipath_tracer_b200/include -Iinclude $< -o $@ \
+	    -Lpath_tracer_b200/lib -lptb200 -Wl,-rpath,'$$ORIGIN/../path_tracer_b200/lib'
+else
+host:
+	@echo "host: $(REFERENCE) not present; keeping prebuilt build/sycl-rt-b200 as is"
+endif
+
 clean:
 	rm -f $(LIB) oracle/libpt_oracle.so
 
-.PHONY: all lib oracle clean
+.PHONY: all lib oracle host clean
