@@ -22,6 +22,9 @@ namespace {
 
 thread_local std::string g_error;
 int g_num_gpus = 1;
+int g_team_size_override = 0;
+int g_n_express = -1;   // < 0: automatic (pt_debug_set_express)
+int g_kernel_kind = 0;  // 0 = wavefront kernel, 1 = lane kernel (pt_debug_set_kernel)
 pt_stats g_stats {};
 
 int fail(int code, const std::string& msg) {
@@ -40,6 +43,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kCounterSlots = 64;
+constexpr unsigned kHeavyCap = 32768;  // entries of the heavy-pixel hand-off queue
 constexpr int kCounterWords = 8;  // [0] scans, [1] first CTA start (ns), [2] queue ran dry (ns), [3] last warp retired (ns)
 
 }  // namespace
@@ -54,6 +58,10 @@ struct pt_device_scene {
   SceneDesc desc {};
   unsigned long long* queue_heads = nullptr;  // kCounterSlots work-queue heads
   unsigned long long* counters = nullptr;     // [0] scans, [1] paths
+  unsigned int* heavy_ctrl = nullptr;
+  unsigned int* heavy_ready = nullptr;
+  float* heavy_entries = nullptr;
+  unsigned int launch_stamp = 0;
   int next_slot = 0;
   unsigned long long paths_launched = 0;
   LaunchInfo last_launch {};
@@ -110,9 +118,14 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   const size_t o_tex = place(host, ps.textures);
   const size_t o_heads = align_up(host.size(), 256);
   host.resize(o_heads + sizeof(unsigned long long) * (kCounterSlots + kCounterWords), 0);
+  const size_t o_hctrl = align_up(host.size(), 256);
+  host.resize(o_hctrl + 64, 0);
+  const size_t o_hready = align_up(host.size(), 256);
+  host.resize(o_hready + sizeof(unsigned) * kHeavyCap, 0);
   const size_t o_bytes = align_up(host.size(), 256);
   const size_t tex_bytes = std::max<size_t>((size_t)scene->n_texture_bytes, 3);
-  const size_t total = o_bytes + align_up(tex_bytes, 256);
+  const size_t o_hentries = o_bytes + align_up(tex_bytes, 256);
+  const size_t total = o_hentries + sizeof(float) * kHeavyEntryWords * (size_t)kHeavyCap;
 
   PT_CUDA(cudaSetDevice(device));
   auto* ds = new pt_device_scene;
@@ -167,6 +180,9 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   d.n_textures = (uint32_t)ps.textures.size();
   ds->queue_heads = reinterpret_cast<unsigned long long*>(ds->arena + o_heads);
   ds->counters = ds->queue_heads + kCounterSlots;
+  ds->heavy_ctrl = reinterpret_cast<unsigned int*>(ds->arena + o_hctrl);
+  ds->heavy_ready = reinterpret_cast<unsigned int*>(ds->arena + o_hready);
+  ds->heavy_entries = reinterpret_cast<float*>(ds->arena + o_hentries);
   *out = ds;
   return PT_OK;
 }
@@ -254,9 +270,19 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   scene->next_slot = (slot + 1) % kCounterSlots;
   p.pixel_counter = scene->queue_heads + slot;
   p.counters = scene->counters;
+  p.team_size = g_team_size_override;  // 0 = chosen from the pixel count at launch
+  p.kernel_kind = g_kernel_kind;
+  p.pool_cap = 0;
+  p.scramble = 1;
+  p.n_express = g_n_express;
+  p.heavy.ctrl = scene->heavy_ctrl, p.heavy.ready = scene->heavy_ready, p.heavy.entries = scene->heavy_entries;
+  p.heavy.cap = kHeavyCap, p.heavy.stamp = ++scene->launch_stamp;
+  PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
   PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 1, 0xff, 2 * sizeof(unsigned long long), st));
-  PT_CUDA(cudaMemsetAsync(p.counters + 3, 0, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 3, 0, 2 * sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 5, 0xff, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 6, 0, sizeof(unsigned long long), st));
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
   scene->paths_launched += (unsigned long long)region->w * region->h * spp;
@@ -267,8 +293,10 @@ int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* sc
   if (!scene) return fail(PT_ERR_INVALID_ARGUMENT, "pt_scene_read_counters: null scene");
   PT_CUDA(cudaSetDevice(scene->device));
   PT_CUDA(cudaDeviceSynchronize());
-  unsigned long long v = 0;
-  PT_CUDA(cudaMemcpy(&v, scene->counters, sizeof v, cudaMemcpyDeviceToHost));
+  unsigned long long all[5] = { 0, 0, 0, 0, 0 };
+  PT_CUDA(cudaMemcpy(all, scene->counters, sizeof all, cudaMemcpyDeviceToHost));
+  const unsigned long long v = all[0];
+  if (all[4] != 0) return fail(PT_ERR_CUDA, "render kernel: the heavy-pixel hand-off queue timed out (internal error)");
   if (paths) *paths = scene->paths_launched;
   if (scans) *scans = v;
   if (reset) {
@@ -278,14 +306,36 @@ int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* sc
   return PT_OK;
 }
 
+// Debug aid (not part of pt_abi.h): force the launch team size (0 = automatic).
+int pt_debug_set_team_size(int t) {
+  g_team_size_override = t;
+  return PT_OK;
+}
+
+// Debug aid (not part of pt_abi.h): 0 = wavefront kernel (default), 1 = lane kernel.
+int pt_debug_set_kernel(int kind) {
+  g_kernel_kind = kind;
+  return PT_OK;
+}
+
+// Debug aid (not part of pt_abi.h): number of express CTAs of the wavefront kernel (< 0 = automatic).
+int pt_debug_set_express(int n) {
+  g_n_express = n;
+  return PT_OK;
+}
+
 // Debug aid (not part of pt_abi.h): timeline of the LAST launch on this scene, in ns:
 // out[0] = queue-dry - start, out[1] = last-warp-retired - start.
-int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[2]) {
+int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[5]) {
   PT_CUDA(cudaSetDevice(scene->device));
   PT_CUDA(cudaDeviceSynchronize());
-  unsigned long long v[4];
+  unsigned long long v[8];
   PT_CUDA(cudaMemcpy(v, scene->counters, sizeof v, cudaMemcpyDeviceToHost));
+  unsigned int ctrl[4];
+  PT_CUDA(cudaMemcpy(ctrl, scene->heavy_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
   out[0] = v[2] - v[1], out[1] = v[3] - v[1];
+  out[2] = v[5] - v[1], out[3] = v[6] - v[1];  // first / last CTA out of regular work
+  out[4] = ctrl[1];                            // heavy pixels handed to the express lane
   return PT_OK;
 }
 

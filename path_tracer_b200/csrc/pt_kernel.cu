@@ -3,25 +3,32 @@
 // persistent sm_100a kernel.
 //
 // Execution model (B200-first, not a translation of the SYCL kernel):
-//   * Persistent CTAs; every LANE owns one pixel at a time and walks that
-//     pixel's `spp` samples serially -- the xorshift32 stream of a pixel is
-//     consumed in a data-dependent way (render.hpp:95-101), so samples of one
-//     pixel cannot be split.  When a pixel is finished the lane pulls the next
-//     pixel index from a global atomic queue ("path regeneration"), so all 32
-//     lanes re-converge at the closest-hit scan with live rays until the
-//     queue runs dry.
-//   * The closest-hit scan (render.hpp:30-51) is the hot loop.  The scene's
-//     scan blob (pt_packed.h) is staged into shared memory with one
-//     cp.async.bulk (TMA) per CTA and streamed with warp-broadcast LDS.128.
-//     Sphere tests are split in two: a branch-free discriminant pass over a
-//     chunk of 32 spheres that only records a per-lane candidate bitmask, and
-//     an exact root pass (sqrt, IEEE division, range and tie rules) over the
-//     few set bits.  Only `t` and the object id are tracked; the full
-//     hit_record (point, normal, face, u, v) is rebuilt once, for the winner.
-//   * Shading (material scatter / emission / textures) is divergent by
-//     nature; it is short compared with the scan and runs per lane.
-// All arithmetic follows the operation order of the reference; see
-// pt_device.cuh for the numerics contract.
+//   * Persistent CTAs.  A pixel's `spp` samples are inherently serial -- its xorshift32 stream is
+//     consumed in a data-dependent way (render.hpp:95-101) -- so the unit of work is a PIXEL, pulled
+//     from a global atomic queue; a finished pixel is replaced at once ("path regeneration") and
+//     the warp re-converges at the closest-hit scan with live rays.
+//   * A warp holds k pixels, k = 32 / T, each owned by a TEAM of T lanes that carry the pixel's
+//     path state REPLICATED (same inputs, same instructions => same values, no communication).
+//     T = 1 in steady state.  The scan (render.hpp:30-51) is split inside a team: member m tests
+//     objects m, m+T, ...; the members' winners are merged with shuffles under the rule
+//     (minimum t, then maximum key) that reproduces the sequential scan's tie behaviour exactly
+//     (pt_packed.h), so the result is bit-identical for every T.  When the queue has run dry and
+//     at most half of a warp's teams still own a pixel, the survivors are RE-PACKED into teams
+//     twice as large: the image's deepest pixels (paths bouncing dozens of times inside glass hold
+//     ten times the average work) are traced with ever shorter rounds instead of sitting on a
+//     serial critical path, and a GPU with few pixels per lane (multi-GPU strong scaling) starts
+//     with T > 1.
+//   * The scene's scan blob (pt_packed.h) is staged into shared memory with cp.async.bulk (TMA)
+//     once per CTA and streamed with broadcast LDS.128.  Sphere tests are two-phase: a branch-free
+//     discriminant pass that only records a per-lane candidate bitmask, and an exact root pass
+//     (sqrt, IEEE division, range and tie rules) over the few set bits.  Only `t` and the object
+//     id are tracked; the full hit_record is rebuilt once, for the winner.
+//   * Shading (material scatter / emission / textures) is divergent by nature; it is short
+//     compared with the scan.  Everything outside the scan loops is kept small (out-of-line
+//     division, square root and trigonometry; table-driven box) because the loops must own the
+//     instruction cache.
+// All arithmetic follows the operation order of the reference; see pt_device.cuh for the
+// numerics contract.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,23 +46,10 @@ constexpr float kTMin = 0.001f;  // render.hpp:40
 #define PT_SCAN_UNROLL 4
 #endif
 constexpr int kScanUnroll = PT_SCAN_UNROLL;  // spheres per hot-loop trip
-#ifndef PT_BOOST_ROUNDS
-#define PT_BOOST_ROUNDS 0
+#ifndef PT_MIN_PIXELS_PER_TEAM
+#define PT_MIN_PIXELS_PER_TEAM 3
 #endif
-#ifndef PT_HEAVY_PER_SAMPLE
-#define PT_HEAVY_PER_SAMPLE 8
-#endif
-constexpr int kBoostRounds = PT_BOOST_ROUNDS;        // short rounds for heavy pixels between two normal rounds
-constexpr int kHeavyPerSample = PT_HEAVY_PER_SAMPLE;  // a pixel is heavy above this many scans per sample ...
-constexpr int kHeavyBase = 32;                        // ... plus this head start
-#ifndef PT_RAMP_BETA
-#define PT_RAMP_BETA 0.0f
-#endif
-constexpr float kRampBeta = PT_RAMP_BETA;  // ramp-down starts when remaining pixels < 32 * warps * beta
-#ifndef PT_TEAM_MAX_LIVE
-#define PT_TEAM_MAX_LIVE 16
-#endif
-constexpr int kTeamMaxLive = PT_TEAM_MAX_LIVE;  // at or below this many live lanes the warp scans in teams
+constexpr int kMinPixelsPerTeam = PT_MIN_PIXELS_PER_TEAM;  // launch with larger teams below this many pixels per team
 
 PT_DEV unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -284,84 +278,112 @@ PT_DEV bool medium_hit_t(const MediumRec& m, const Ray& r, float tmin, float tma
 }
 
 // ---------------------------------------------------------------- the scan
-// render.hpp:30-51.  `live` lanes carry a real ray; the others ride along so
-// that the warp stays converged on the broadcast loads.
+// Merge the members' partial winners: afterwards every member of a team holds the team's winner.
+PT_DEV void team_merge(const SceneDesc& sc, Best& best, int team_size) {
+  for (int o = team_size >> 1; o > 0; o >>= 1) {
+    const float ot = __shfl_xor_sync(0xffffffffu, best.t, o);
+    const int oid = __shfl_xor_sync(0xffffffffu, best.id, o);
+    if (oid >= 0) {
+      if (best.id < 0 || ot < best.t)
+        best.t = ot, best.id = oid;
+      else if (ot == best.t && oid != best.id && key_of(sc, oid) > key_of(sc, best.id))
+        best.id = oid;
+    }
+  }
+}
+
+// Two-phase sphere scan over elements first, first+stride, ... < end (kMoving: 2 float4 per sphere).
+// Phase 1 is branch-free and only collects a bitmask of spheres whose discriminant is positive;
+// phase 2 computes exact roots for the set bits.  The stride-1 instance is the steady-state hot
+// loop (4 spheres per trip so that it stays inside the instruction cache).
+template <bool kSmem, bool kMoving>
+PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, int first, int end, int stride,
+                         const Ray& r, float a, float f, bool act, int type, Best& best) {
+  auto center = [&](int i, float& cx, float& cy, float& cz, float& r2) {
+    if constexpr (kMoving) {
+      const float4 s = ld4<kSmem>(data + 2 * i);
+      const float4 v = ld4<kSmem>(data + 2 * i + 1);
+      cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2 = s.w;  // sphere.hpp:55
+    } else {
+      const float4 s = ld4<kSmem>(data + i);
+      cx = s.x, cy = s.y, cz = s.z, r2 = s.w;
+    }
+  };
+  auto positive = [&](int i) {
+    float cx, cy, cz, r2;
+    center(i, cx, cy, cz, r2);
+    const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
+    const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
+    const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
+    return fsub(fmul(b, b), fmul(a, c)) > 0.f;
+  };
+  if (stride == 1) {
+    // group sizes are padded to kSphereChunk with spheres that can never be hit (pt_pack.cpp)
+#pragma unroll 1
+    for (int base = first; base < end; base += kSphereChunk) {
+      uint32_t mask = 0;
+#pragma unroll 1
+      for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
+        uint32_t nib = 0;
+#pragma unroll
+        for (int j = 0; j < kScanUnroll; ++j)
+          if (positive(base + it + j)) nib |= (1u << j);
+        mask |= nib << it;
+      }
+      if (!act) mask = 0;
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float cx, cy, cz, r2;
+        center(base + j, cx, cy, cz, r2);
+        sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, base + j));
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int base = first; base < end; base += kSphereChunk * stride) {
+      uint32_t mask = 0;
+#pragma unroll 2
+      for (int it = 0; it < kSphereChunk; ++it) {
+        const int i = base + it * stride;
+        if (i < end && positive(i)) mask |= (1u << it);
+      }
+      if (!act) mask = 0;
+      while (mask) {
+        const int it = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int i = base + it * stride;
+        float cx, cy, cz, r2;
+        center(i, cx, cy, cz, r2);
+        sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, i));
+      }
+    }
+  }
+}
+
+// render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
+// of each group.  `act`: this lane's team carries a real ray (the others ride along so that the
+// warp stays converged on the shared loads and the shuffles).
 template <bool kSmem>
-PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, bool live) {
+PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, bool act, int member,
+                        int team_size) {
   Best best { kInf, -1 };
   const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant
   const int n_groups = (int)sc.n_groups;
   for (int gi = 0; gi < n_groups; ++gi) {
     const Group g = sv.groups[gi];
+    const int first = g.begin + member, end = g.begin + g.count;
     switch (g.type) {
-      case G_SPHERE: {
-#pragma unroll 1
-        for (int base = g.begin; base < g.begin + g.count; base += kSphereChunk) {
-          const float4* __restrict__ p = sv.sphere + base;
-          uint32_t mask = 0;
-          // Branch-free discriminant pass; kScanUnroll spheres per loop trip keeps
-          // the hot loop inside the instruction cache (DESIGN.md "scan loop").
-#pragma unroll 1
-          for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
-            uint32_t nib = 0;
-#pragma unroll
-            for (int j = 0; j < kScanUnroll; ++j) {
-              const float4 s = ld4<kSmem>(p + it + j);
-              const float ocx = fsub(r.o.x, s.x), ocy = fsub(r.o.y, s.y), ocz = fsub(r.o.z, s.z);
-              const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-              const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), s.w);
-              const float disc = fsub(fmul(b, b), fmul(a, c));
-              if (disc > 0.f) nib |= (1u << j);
-            }
-            mask |= nib << it;
-          }
-          if (!live) mask = 0;
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 s = ld4<kSmem>(p + j);
-            sphere_roots_scan(sc, best, r, a, s.x, s.y, s.z, s.w, make_id(G_SPHERE, base + j));
-          }
-        }
+      case G_SPHERE:
+        scan_spheres<kSmem, false>(sc, sv.sphere, first, end, team_size, r, a, 0.f, act, G_SPHERE, best);
         break;
-      }
-      case G_MOVING_SPHERE: {
-        const float f = fdiv(fsub(r.tm, g.time0), g.den);  // sphere.hpp:55
-#pragma unroll 1
-        for (int base = g.begin; base < g.begin + g.count; base += kSphereChunk) {
-          const float4* __restrict__ p = sv.moving + 2 * base;
-          uint32_t mask = 0;
-#pragma unroll 1
-          for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
-            uint32_t nib = 0;
-#pragma unroll
-            for (int j = 0; j < kScanUnroll; ++j) {
-              const float4 s = ld4<kSmem>(p + 2 * (it + j));
-              const float4 v = ld4<kSmem>(p + 2 * (it + j) + 1);
-              const float cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z));
-              const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
-              const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-              const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), s.w);
-              const float disc = fsub(fmul(b, b), fmul(a, c));
-              if (disc > 0.f) nib |= (1u << j);
-            }
-            mask |= nib << it;
-          }
-          if (!live) mask = 0;
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float4 s = ld4<kSmem>(p + 2 * j);
-            const float4 v = ld4<kSmem>(p + 2 * j + 1);
-            const float cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z));
-            sphere_roots_scan(sc, best, r, a, cx, cy, cz, s.w, make_id(G_MOVING_SPHERE, base + j));
-          }
-        }
+      case G_MOVING_SPHERE:
+        scan_spheres<kSmem, true>(sc, sv.moving, first, end, team_size, r, a, fdiv(fsub(r.tm, g.time0), g.den), act,
+                                  G_MOVING_SPHERE, best);
         break;
-      }
       case G_RECT: {
-        if (live)
-          for (int i = g.begin; i < g.begin + g.count; ++i) {
+        if (act)
+          for (int i = first; i < end; i += team_size) {
             const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
             const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
             float t, ra, rb;
@@ -371,8 +393,8 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
         break;
       }
       case G_TRIANGLE: {
-        if (live)
-          for (int i = g.begin; i < g.begin + g.count; ++i) {
+        if (act)
+          for (int i = first; i < end; i += team_size) {
             const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
             const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
             const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
@@ -383,8 +405,8 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
         break;
       }
       case G_BOX: {
-        if (live)
-          for (int i = g.begin; i < g.begin + g.count; ++i) {
+        if (act)
+          for (int i = first; i < end; i += team_size) {
             const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
             const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
             float t, ra, rb;
@@ -393,8 +415,11 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
           }
         break;
       }
-      default: {  // G_MEDIUM: sees the running closest of every lower-index object, commits unconditionally
-        if (live) {
+      default: {
+        // G_MEDIUM sees the running closest hit of EVERY lower-index object (merge first) and commits
+        // unconditionally; every member replays the RNG draw on its replica of the generator.
+        if (team_size > 1) team_merge(sc, best, team_size);
+        if (act) {
           float t;
           if (medium_hit_t(sc.media[g.begin], r, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
         }
@@ -402,136 +427,8 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       }
     }
   }
+  if (team_size > 1) team_merge(sc, best, team_size);
   return best;
-}
-
-
-// ---------------------------------------------------------------- team scan (tail mode)
-// When only k < 32 lanes of a warp still own a pixel (the work queue has run
-// dry), one ray per lane would leave most of the warp idle and -- worse --
-// leave the deepest paths of the image on a serial critical path.  The warp
-// is then split into teams of T = 32 / pow2ceil(k) lanes, one team per live
-// ray: member m of a team tests objects m, m+T, ... exactly, and the members'
-// winners are merged with the same (minimum t, maximum key) rule, so the
-// result is bit-identical to the per-lane scan for any T.  A constant_medium
-// still sees the running closest hit of ALL lower-index objects: the team
-// merges before evaluating it, and every member replays its RNG draw on a copy
-// of the owner's generator.
-struct KeyedBest {
-  float t;
-  int id;
-  int key;
-};
-
-PT_DEV void offer(KeyedBest& m, float t, int id, int key) {
-  if (t < m.t || (t == m.t && key > m.key) || m.id < 0) m.t = t, m.id = id, m.key = key;
-}
-// rect / triangle / box let NaN through their range test (rectangle.hpp:36)
-PT_DEV void offer_le(KeyedBest& m, float t, int id, int key) {
-  if (!(t == m.t) || key > m.key || m.id < 0) m.t = t, m.id = id, m.key = key;
-}
-
-PT_DEV void team_merge(KeyedBest& m, int team_size) {
-  for (int o = team_size >> 1; o > 0; o >>= 1) {
-    const float ot = __shfl_xor_sync(0xffffffffu, m.t, o);
-    const int oid = __shfl_xor_sync(0xffffffffu, m.id, o);
-    const int okey = __shfl_xor_sync(0xffffffffu, m.key, o);
-    if (oid >= 0 && (m.id < 0 || ot < m.t || (ot == m.t && okey > m.key))) m.t = ot, m.id = oid, m.key = okey;
-  }
-}
-
-PT_DEV void team_sphere(KeyedBest& m, const Ray& r, float a, float cx, float cy, float cz, float r2, int id,
-                        const SphereAux* aux) {
-  const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
-  const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-  const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
-  const float disc = fsub(fmul(b, b), fmul(a, c));
-  if (!(disc > 0.f) || (b > 0.f && c > 0.f)) return;
-  const float sq = fsqrt(disc);
-  const float t0 = fdiv(fsub(-b, sq), a);
-  if (t0 < kInf && t0 > kTMin) {
-    if (t0 <= m.t || m.id < 0) offer(m, t0, id, aux->key);
-    return;
-  }
-  const float t1 = fdiv(fadd(-b, sq), a);
-  if (t1 < kInf && t1 > kTMin && (t1 <= m.t || m.id < 0)) offer(m, t1, id, aux->key);
-}
-
-// `member` in [0, team_size); `active` = this team carries a live ray.
-template <bool kSmem>
-PT_DEV Best team_closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, int member,
-                             int team_size, bool active) {
-  KeyedBest m { kInf, -1, 0 };
-  const float a = vdot(r.d, r.d);
-  const int n_groups = (int)sc.n_groups;
-  for (int gi = 0; gi < n_groups; ++gi) {
-    const Group g = sv.groups[gi];
-    const int end = active ? g.begin + g.count : 0;
-    switch (g.type) {
-      case G_SPHERE: {
-#pragma unroll 1
-        for (int i = g.begin + member; i < end; i += team_size) {
-          const float4 s = ld4<kSmem>(sv.sphere + i);
-          team_sphere(m, r, a, s.x, s.y, s.z, s.w, make_id(G_SPHERE, i), sc.sphere_aux + i);
-        }
-        break;
-      }
-      case G_MOVING_SPHERE: {
-        const float f = fdiv(fsub(r.tm, g.time0), g.den);
-#pragma unroll 1
-        for (int i = g.begin + member; i < end; i += team_size) {
-          const float4 s = ld4<kSmem>(sv.moving + 2 * i);
-          const float4 v = ld4<kSmem>(sv.moving + 2 * i + 1);
-          const float cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z));
-          team_sphere(m, r, a, cx, cy, cz, s.w, make_id(G_MOVING_SPHERE, i), sc.moving_aux + i);
-        }
-        break;
-      }
-      case G_RECT: {
-#pragma unroll 1
-        for (int i = g.begin + member; i < end; i += team_size) {
-          const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
-          const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
-          float t, ra, rb;
-          if (rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, m.t, t, ra, rb))
-            offer_le(m, t, make_id(G_RECT, i), sc.rect_aux[i].key);
-        }
-        break;
-      }
-      case G_TRIANGLE: {
-#pragma unroll 1
-        for (int i = g.begin + member; i < end; i += team_size) {
-          const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
-          const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
-          const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
-          float t;
-          if (triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, m.t, t))
-            offer_le(m, t, make_id(G_TRIANGLE, i), sc.tri_aux[i].key);
-        }
-        break;
-      }
-      case G_BOX: {
-#pragma unroll 1
-        for (int i = g.begin + member; i < end; i += team_size) {
-          const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
-          const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
-          float t, ra, rb;
-          if (box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, m.t, t, ra, rb) >= 0)
-            offer_le(m, t, make_id(G_BOX, i), sc.box_aux[i].key);
-        }
-        break;
-      }
-      default: {
-        team_merge(m, team_size);  // every member now holds the running closest hit of all lower-index objects
-        float t;
-        if (active && medium_hit_t(sc.media[g.begin], r, kTMin, m.id < 0 ? kInf : m.t, rng, t))
-          m.t = t, m.id = make_id(G_MEDIUM, g.begin), m.key = sc.media[g.begin].key;
-        break;
-      }
-    }
-  }
-  team_merge(m, team_size);
-  return Best { m.id < 0 ? kInf : m.t, m.id };
 }
 
 // ---------------------------------------------------------------- shading
@@ -669,6 +566,82 @@ PT_DEV V3 textured(const SceneDesc& sc, int tex, HitRec& rec) {
 
 }  // namespace
 
+// render.hpp:96-99 + camera.hpp:93-100: one camera sample for pixel (px, py); 5 RNG draws
+PT_DEV void camera_ray(const pt_camera& cam, int px, int py, float fwidth, float fheight, Rng& rng, Ray& ray) {
+  const float u = fdiv(fadd((float)px, rng_float(rng)), fwidth);
+  const float v = fdiv(fadd((float)py, rng_float(rng)), fheight);
+  float dx, dy;
+  rng_in_unit_disk(rng, dx, dy);
+  const V3 rd = v3(fmul(cam.lens_radius, dx), fmul(cam.lens_radius, dy), fmul(cam.lens_radius, 0.f));
+  const V3 cu = vld(cam.u), cv = vld(cam.v);
+  const V3 offset = vadd(v3(fmul(cu.x, rd.x), fmul(cu.y, rd.x), fmul(cu.z, rd.x)),
+                         v3(fmul(cv.x, rd.y), fmul(cv.y, rd.y), fmul(cv.z, rd.y)));
+  const V3 origin = vld(cam.origin);
+  ray.o = vadd(origin, offset);
+  ray.d = vsub(vsub(vadd(vadd(vld(cam.lower_left_corner), vscale(u, vld(cam.horizontal))),
+                         vscale(v, vld(cam.vertical))),
+                    origin),
+               offset);
+  ray.tm = rng_range(rng, cam.time0, cam.time1);
+}
+
+// One iteration of get_color's depth loop after the closest-hit scan (render.hpp:58-91): sky,
+// emission or scatter.  Returns true when the path ends; `contribution` is what it adds to the pixel.
+PT_DEV bool shade(const SceneDesc& sc, const SceneView& sv, int depth, bool smem, const Best& best, Ray& ray,
+                  Rng& rng, V3& att, int& bounce, V3& contribution) {
+  contribution = v3(0.f, 0.f, 0.f);
+  if (best.id < 0) {
+    // background gradient, render.hpp:83-87
+    const V3 ud = unit_vector(ray.d);
+    const float hit_pt = fmul(0.5f, fadd(ud.y, 1.0f));
+    const float w0 = fsub(1.0f, hit_pt);
+    const V3 c = vadd(v3(fmul(w0, 1.0f), fmul(w0, 1.0f), fmul(w0, 1.0f)),
+                      v3(fmul(hit_pt, 0.5f), fmul(hit_pt, 0.7f), fmul(hit_pt, 1.0f)));
+    contribution = vmul(att, c);
+    return true;
+  }
+  HitRec rec;
+  const int mat_index = build_record(sc, sv, ray, best, rec, smem);
+  const pt_material* m = reinterpret_cast<const pt_material*>(sc.materials) + mat_index;
+  const int kind = m->kind;
+  bool scattered_ok = true;
+  Ray scattered;
+  scattered.o = rec.p;
+  scattered.tm = ray.tm;
+  if (kind == PT_MAT_LAMBERTIAN) {  // material.hpp:18-28
+    scattered.d = vadd(rec.normal, rng_unit_vec(rng));
+    att = vmul(att, textured(sc, m->texture, rec));
+  } else if (kind == PT_MAT_METAL) {  // material.hpp:39-48
+    const V3 reflected = reflect(unit_vector(ray.d), rec.normal);
+    scattered.d = vadd(reflected, vscale(m->param, rng_in_unit_ball(rng)));
+    att = vmul(att, vld(m->albedo));
+    scattered_ok = vdot(scattered.d, rec.normal) > 0.f;
+  } else if (kind == PT_MAT_DIELECTRIC) {  // material.hpp:68-88
+    att = vmul(att, vld(m->albedo));
+    const float ref_idx = m->param;
+    const float refraction_ratio = rec.front_face ? fdiv(1.0f, ref_idx) : ref_idx;
+    const V3 unit_direction = unit_vector(ray.d);
+    const float cos_theta = fminf(-vdot(unit_direction, rec.normal), 1.0f);
+    const float sin_theta = fsqrt(fsub(1.0f, fmul(cos_theta, cos_theta)));
+    const bool cannot_refract = fmul(refraction_ratio, sin_theta) > 1.0f;
+    // short-circuit: the RNG is only drawn when refraction is possible
+    if (cannot_refract || reflectance(cos_theta, refraction_ratio) > rng_float(rng))
+      scattered.d = reflect(unit_direction, rec.normal);
+    else
+      scattered.d = refract(unit_direction, rec.normal, refraction_ratio);
+  } else if (kind == PT_MAT_LIGHTSOURCE) {  // material.hpp:104-108
+    contribution = textured(sc, m->texture, rec);  // emitted, NOT attenuated (render.hpp:73)
+    scattered_ok = false;
+  } else {  // isotropic, material.hpp:119-126
+    scattered.d = rng_in_unit_ball(rng);
+    att = vmul(att, textured(sc, m->texture, rec));
+  }
+  if (!scattered_ok) return true;  // render.hpp:73 (emitted is zero for everything but lights)
+  ray = scattered;
+  ++bounce;
+  return bounce == depth;  // render.hpp:91: out of depth -> black
+}
+
 // ---------------------------------------------------------------- the kernel
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(const RenderParams p) {
@@ -706,55 +679,68 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
   const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
 
-  // per-lane path state
-  bool live = false;          // owns a pixel
-  bool need_path = true;      // must start a new camera sample
-  int px = 0, py = 0;         // global pixel coordinates
+  // per-lane path state, replicated across the lanes of a team
+  const int lane = (int)(threadIdx.x & 31u);
+  int team_size = p.team_size;        // lanes per pixel (power of two); grows when the warp is re-packed
+  int member = lane & (team_size - 1);
+  bool live = false;                  // owns a pixel
+  bool need_path = true;              // must start a new camera sample
+  bool exhausted_queue = false;       // the pixel queue has run dry
+  int px = 0, py = 0;                 // global pixel coordinates
   float* out_px = nullptr;
-  int sample = p.spp;         // == spp forces a pixel fetch first
+  int sample = p.spp;
   int bounce = 0;
   Rng rng { 0u };
   Ray ray { v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), 0.f };
   V3 att = v3(1.f, 1.f, 1.f);
   V3 acc = v3(0.f, 0.f, 0.f);
   unsigned int n_scans = 0;
-  unsigned int pix_scans = 0;  // closest-hit scans spent on the current pixel
-  bool exhausted_queue = false;
-  int warp_cap = 32;  // pixels this warp may hold (ramp-down at the end of the queue)
-  const unsigned long long ramp_div =
-      max(1ull, (unsigned long long)((float)(gridDim.x * (blockDim.x >> 5)) * kRampBeta));
 
-  for (unsigned iter = 0;; ++iter) {
-    // Boost rounds: the image's deepest pixels (paths bouncing dozens of times inside glass) hold
-    // ten times the average work and, one bounce per full-cost round, would sit on a serial
-    // critical path longer than the whole frame.  Between two normal rounds the warp therefore
-    // runs kBoostRounds short rounds for its HEAVY pixels only, scanned by lane teams.
-    const bool boost = (iter % (unsigned)(kBoostRounds + 1)) != 0u;
-    const bool heavy = live && pix_scans > (unsigned)(kHeavyBase + kHeavyPerSample * sample);
-    if (boost && !__any_sync(0xffffffffu, heavy)) continue;
-    const bool part = !boost || heavy;  // this lane takes part in this round
+  for (;;) {
+    // ---- (R) re-pack: the queue is dry for this warp and at most half of its teams still own a
+    // pixel -> move the survivors into teams twice (or more) as large.
+    if (team_size < 32) {
+      const unsigned can_fetch = __ballot_sync(0xffffffffu, !live && !exhausted_queue);
+      const unsigned leaders = __ballot_sync(0xffffffffu, live && member == 0);
+      const int k_live = __popc(leaders);
+      if (can_fetch == 0u && k_live > 0 && 2 * k_live * team_size <= 32) {
+        int new_size = team_size;
+        while (2 * k_live * new_size <= 32) new_size <<= 1;
+        const int new_team = lane / new_size;
+        const bool keep = new_team < k_live;
+        const int src = keep ? (int)__fns(leaders, 0u, new_team + 1) : lane;  // leader lane of the new_team-th live team
+#define PT_MOVE(x) x = __shfl_sync(0xffffffffu, x, src)
+        PT_MOVE(px), PT_MOVE(py), PT_MOVE(sample), PT_MOVE(bounce), PT_MOVE(rng.s);
+        PT_MOVE(ray.o.x), PT_MOVE(ray.o.y), PT_MOVE(ray.o.z), PT_MOVE(ray.d.x), PT_MOVE(ray.d.y), PT_MOVE(ray.d.z);
+        PT_MOVE(ray.tm), PT_MOVE(att.x), PT_MOVE(att.y), PT_MOVE(att.z), PT_MOVE(acc.x), PT_MOVE(acc.y), PT_MOVE(acc.z);
+        unsigned long long optr = (unsigned long long)out_px;
+        PT_MOVE(optr);
+        out_px = (float*)optr;
+        int np = need_path ? 1 : 0;
+        PT_MOVE(np);
+        need_path = np != 0;
+#undef PT_MOVE
+        live = keep;
+        exhausted_queue = true;
+        team_size = new_size;
+        member = lane & (team_size - 1);
+      }
+    }
 
     // ---- (A) path regeneration: render.hpp:94-105 sample loop, :130-133 seeding
-    // A pixel is finished when its last sample ended: write it out (render.hpp:102-105).
-    if (need_path && live && part && sample == p.spp) {
+    if (need_path && live && sample == p.spp) {
+      // final_color /= samples; fb[y][x] = final_color (render.hpp:102-105); one writer per team
       const V3 fin = vdivs(acc, fspp);
-      out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+      if (member == 0) out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
       live = false;
     }
-    // Pixel fetch with ramp-down: while plenty of pixels remain every lane holds one (cap 32).
-    // Towards the end of the queue a warp may only hold `cap` pixels, cap halving as the queue
-    // drains, so that the pixels still in flight are scanned by ever larger lane teams (shorter
-    // per-pixel latency) instead of leaving a long tail of nearly idle warps.
     {
-      const bool wants = need_path && !live && !exhausted_queue && !boost;
-      const unsigned want_mask = __ballot_sync(0xffffffffu, wants);
-      if (want_mask != 0u) {
-        const unsigned busy_mask = __ballot_sync(0xffffffffu, live);
-        const int room = warp_cap - __popc(busy_mask);
-        const int my_rank = __popc(want_mask & ((1u << (threadIdx.x & 31u)) - 1u));
-        unsigned fetched_pos = 0u;
-        if (wants && my_rank < room) {
-          const unsigned long long idx = atomicAdd(p.pixel_counter, 1ull);
+      const bool wants = need_path && !live && !exhausted_queue;
+      if (__any_sync(0xffffffffu, wants)) {
+        unsigned long long idx = 0ull;
+        if (wants && member == 0) idx = atomicAdd(p.pixel_counter, 1ull);  // the team leader pulls the next pixel
+        idx = __shfl_sync(0xffffffffu, idx, lane - member);
+        if (wants) {
           if (idx < n_pixels) {
             const int k = (int)(idx / (unsigned long long)p.region.w);
             const int xx = (int)(idx - (unsigned long long)k * (unsigned long long)p.region.w);
@@ -765,140 +751,30 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
             rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
             acc = v3(0.f, 0.f, 0.f);
             sample = 0;
-            pix_scans = 0u;
             live = true;
-            fetched_pos = (unsigned)min(idx + 1ull, 0xffffffffull);
           } else {
             exhausted_queue = true;
-            fetched_pos = 0xffffffffu;
-            if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+            if (p.counters && member == 0) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
           }
         }
-        const unsigned seen = __reduce_max_sync(0xffffffffu, fetched_pos);
-        if (seen != 0u) {
-          const unsigned long long remaining = seen >= n_pixels ? 0ull : n_pixels - seen;
-          // pixels a warp may hold = remaining pixels per warp (scaled), rounded down to a power of two
-          const unsigned long long per_warp = remaining / ramp_div;
-          warp_cap = per_warp >= 32ull ? 32 : (per_warp <= 1ull ? 1 : (1 << (31 - __clz((int)per_warp))));
-        }
       }
     }
-    if (need_path && live && part) {
-        // render.hpp:96-99 + camera.hpp:93-100
-        const float u = fdiv(fadd((float)px, rng_float(rng)), fwidth);
-        const float v = fdiv(fadd((float)py, rng_float(rng)), fheight);
-        float dx, dy;
-        rng_in_unit_disk(rng, dx, dy);
-        const V3 rd = v3(fmul(cam.lens_radius, dx), fmul(cam.lens_radius, dy), fmul(cam.lens_radius, 0.f));
-        const V3 cu = vld(cam.u), cv = vld(cam.v);
-        const V3 offset = vadd(v3(fmul(cu.x, rd.x), fmul(cu.y, rd.x), fmul(cu.z, rd.x)),
-                               v3(fmul(cv.x, rd.y), fmul(cv.y, rd.y), fmul(cv.z, rd.y)));
-        const V3 origin = vld(cam.origin);
-        ray.o = vadd(origin, offset);
-        ray.d = vsub(vsub(vadd(vadd(vld(cam.lower_left_corner), vscale(u, vld(cam.horizontal))),
-                               vscale(v, vld(cam.vertical))),
-                          origin),
-                     offset);
-        ray.tm = rng_range(rng, cam.time0, cam.time1);
-        att = v3(1.f, 1.f, 1.f);
-        bounce = 0;
-        need_path = false;
+    if (need_path && live) {
+      camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+      att = v3(1.f, 1.f, 1.f);
+      bounce = 0;
+      need_path = false;
     }
-    if (!boost && !__any_sync(0xffffffffu, live)) break;
-    const bool act = live && part;
-    const unsigned live_mask = __ballot_sync(0xffffffffu, act);  // lanes with a ray to trace this round
-    if (live_mask == 0u) continue;
+    if (!__any_sync(0xffffffffu, live)) break;
 
     // ---- (B) closest hit: render.hpp:60 -> :30-51
-    Best best { kInf, -1 };
-    const int n_live = __popc(live_mask);
-    if (n_live <= kTeamMaxLive) {
-      // few rays: one TEAM of lanes per ray (see team_closest_hit)
-      const int lane = (int)(threadIdx.x & 31u);
-      int team_size = 32;
-      while (team_size * n_live > 32) team_size >>= 1;  // largest power of two with team_size * n_live <= 32
-      const int team = lane / team_size;
-      const bool active = team < n_live;
-      const int owner = active ? (int)__fns(live_mask, 0u, team + 1) : 0;  // lane of the team-th live ray
-      Ray rr;
-      rr.o.x = __shfl_sync(0xffffffffu, ray.o.x, owner), rr.o.y = __shfl_sync(0xffffffffu, ray.o.y, owner);
-      rr.o.z = __shfl_sync(0xffffffffu, ray.o.z, owner), rr.d.x = __shfl_sync(0xffffffffu, ray.d.x, owner);
-      rr.d.y = __shfl_sync(0xffffffffu, ray.d.y, owner), rr.d.z = __shfl_sync(0xffffffffu, ray.d.z, owner);
-      rr.tm = __shfl_sync(0xffffffffu, ray.tm, owner);
-      Rng rg { __shfl_sync(0xffffffffu, rng.s, owner) };
-      const Best b = team_closest_hit<kSmem>(sc, sv, rr, rg, lane % team_size, team_size, active);
-      // hand the result back: the j-th live lane reads from the first lane of team j
-      const int my_team = __popc(live_mask & ((1u << lane) - 1u));
-      const int src = act ? my_team * team_size : 0;
-      const float bt = __shfl_sync(0xffffffffu, b.t, src);
-      const int bid = __shfl_sync(0xffffffffu, b.id, src);
-      const uint32_t brs = __shfl_sync(0xffffffffu, rg.s, src);
-      if (act) best.t = bt, best.id = bid, rng.s = brs;
-    } else {
-      best = closest_hit<kSmem>(sc, sv, ray, rng, act);
-    }
+    const Best best = closest_hit<kSmem>(sc, sv, ray, rng, live, member, team_size);
 
-    // ---- (C) shade: render.hpp:58-91
-    if (act) {
-      ++n_scans;
-      ++pix_scans;
-      V3 contribution = v3(0.f, 0.f, 0.f);
-      bool path_done = false;
-      if (best.id < 0) {
-        // background gradient, render.hpp:83-87
-        const V3 ud = unit_vector(ray.d);
-        const float hit_pt = fmul(0.5f, fadd(ud.y, 1.0f));
-        const float w0 = fsub(1.0f, hit_pt);
-        const V3 c = vadd(v3(fmul(w0, 1.0f), fmul(w0, 1.0f), fmul(w0, 1.0f)),
-                          v3(fmul(hit_pt, 0.5f), fmul(hit_pt, 0.7f), fmul(hit_pt, 1.0f)));
-        contribution = vmul(att, c);
-        path_done = true;
-      } else {
-        HitRec rec;
-        const int mat_index = build_record(sc, sv, ray, best, rec, kSmem);
-        const pt_material* m = reinterpret_cast<const pt_material*>(sc.materials) + mat_index;
-        const int kind = m->kind;
-        bool scattered_ok = true;
-        Ray scattered;
-        scattered.o = rec.p;
-        scattered.tm = ray.tm;
-        if (kind == PT_MAT_LAMBERTIAN) {  // material.hpp:18-28
-          scattered.d = vadd(rec.normal, rng_unit_vec(rng));
-          att = vmul(att, textured(sc, m->texture, rec));
-        } else if (kind == PT_MAT_METAL) {  // material.hpp:39-48
-          const V3 reflected = reflect(unit_vector(ray.d), rec.normal);
-          scattered.d = vadd(reflected, vscale(m->param, rng_in_unit_ball(rng)));
-          att = vmul(att, vld(m->albedo));
-          scattered_ok = vdot(scattered.d, rec.normal) > 0.f;
-        } else if (kind == PT_MAT_DIELECTRIC) {  // material.hpp:68-88
-          att = vmul(att, vld(m->albedo));
-          const float ref_idx = m->param;
-          const float refraction_ratio = rec.front_face ? fdiv(1.0f, ref_idx) : ref_idx;
-          const V3 unit_direction = unit_vector(ray.d);
-          const float cos_theta = fminf(-vdot(unit_direction, rec.normal), 1.0f);
-          const float sin_theta = fsqrt(fsub(1.0f, fmul(cos_theta, cos_theta)));
-          const bool cannot_refract = fmul(refraction_ratio, sin_theta) > 1.0f;
-          // short-circuit: the RNG is only drawn when refraction is possible
-          if (cannot_refract || reflectance(cos_theta, refraction_ratio) > rng_float(rng))
-            scattered.d = reflect(unit_direction, rec.normal);
-          else
-            scattered.d = refract(unit_direction, rec.normal, refraction_ratio);
-        } else if (kind == PT_MAT_LIGHTSOURCE) {  // material.hpp:104-108
-          contribution = textured(sc, m->texture, rec);  // emitted, NOT attenuated (render.hpp:73)
-          scattered_ok = false;
-        } else {  // isotropic, material.hpp:119-126
-          scattered.d = rng_in_unit_ball(rng);
-          att = vmul(att, textured(sc, m->texture, rec));
-        }
-        if (scattered_ok) {
-          ray = scattered;
-          ++bounce;
-          if (bounce == p.depth) path_done = true;  // render.hpp:91, black
-        } else {
-          path_done = true;  // render.hpp:73 (emitted is zero for everything but lights)
-        }
-      }
-      if (path_done) {
+    // ---- (C) shade: render.hpp:58-91 (every member of a team computes the same thing)
+    if (live) {
+      if (member == 0) ++n_scans;
+      V3 contribution;
+      if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
         acc = vadd(acc, contribution);
         ++sample;
         need_path = true;
@@ -914,6 +790,400 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   if ((threadIdx.x & 31) == 0 && p.counters) atomicAdd(p.counters, (unsigned long long)warp_scans);
 }
 
+// ---------------------------------------------------------------- the wavefront kernel
+// Bulk-synchronous wavefront inside one CTA per SM.  The path state of up to kWavePool pixels lives
+// in a structure-of-arrays RAY POOL in shared memory instead of in the registers of fixed lanes, and
+// the CTA alternates between three phases separated by __syncthreads():
+//
+//   SCAN   every live ray gets its closest hit (render.hpp:30-51).  All warps run the same tight
+//          loops at the same time, so the loops own the instruction cache and the issue ports.
+//          With fewer live rays than lanes a ray is scanned by a TEAM of lanes (see closest_hit).
+//   SORT   the rays are counting-sorted by what has to happen next: background, or the kind of the
+//          hit material (the "compact divergent material work" step, done across the CTA).
+//   SHADE  batches of 32 CONSECUTIVE sorted rays are shaded by one warp each, so the lanes of a warp
+//          run the same material code; finished paths start their pixel's next sample (the RNG
+//          stream of a pixel is strictly serial) or write the pixel and pull a new one from the
+//          global pixel queue.
+//
+// HAND-OFF QUEUE.  A pixel's samples are serial and a full round takes tens of microseconds, so the
+// few pixels that hold ten times the average work (paths bouncing dozens of times inside glass:
+// 3 000 scans where the mean is 260) would sit on a critical path longer than the whole frame, and
+// at the end of the frame every CTA would drain its own leftovers alone.  A pixel whose scan rate
+// marks it as HEAVY is therefore handed, with its complete path state, to a global queue.  It is
+// taken over by a CTA that runs SHORT rounds: one of a few EXPRESS CTAs that keep only a handful of
+// rays in flight (each scanned by a team of lanes, a round of a few microseconds), or any CTA whose
+// own pixels have run out -- which also balances the end of the frame across the whole GPU.
+//
+// Results are bit-identical to the lane kernel: the same device functions are called on the same
+// per-pixel state, only the assignment of work to lanes differs.
+#ifndef PT_WAVE_THREADS
+#define PT_WAVE_THREADS 512
+#endif
+#ifndef PT_WAVE_ROUNDS
+#define PT_WAVE_ROUNDS 2
+#endif
+#ifndef PT_HEAVY_RATE
+#define PT_HEAVY_RATE 10
+#endif
+#ifndef PT_HEAVY_RATE_DRY
+#define PT_HEAVY_RATE_DRY 4
+#endif
+#ifndef PT_EXPRESS_CAP
+#define PT_EXPRESS_CAP 64
+#endif
+constexpr int kWaveThreads = PT_WAVE_THREADS;
+constexpr int kWavePool = PT_WAVE_ROUNDS * kWaveThreads;  // pixels (rays) a CTA keeps in flight: whole scan passes
+constexpr int kWaveKinds = 6;                              // 0 = background, 1 + PT_MAT_* otherwise
+constexpr int kHeavyRate = PT_HEAVY_RATE;                  // heavy: more than kHeavyBase + rate * samples scans so far
+constexpr int kHeavyRateDry = PT_HEAVY_RATE_DRY;           // ... a lower bar once the pixel queue is dry (load sharing)
+constexpr int kHeavyBase = 64;
+constexpr int kExpressCap = PT_EXPRESS_CAP;                // rays in flight in a CTA that serves the hand-off queue
+
+struct WavePool {
+  float ox[kWavePool], oy[kWavePool], oz[kWavePool], dx[kWavePool], dy[kWavePool], dz[kWavePool], tm[kWavePool];
+  float hit_t[kWavePool];
+  int hit_id[kWavePool];
+  float att_x[kWavePool], att_y[kWavePool], att_z[kWavePool];
+  float acc_x[kWavePool], acc_y[kWavePool], acc_z[kWavePool];
+  uint32_t rng[kWavePool];
+  uint32_t pix[kWavePool];  // position of the pixel in the work queue
+  int sample[kWavePool];
+  int bounce[kWavePool];
+  int scans[kWavePool];               // closest-hit scans spent on the current pixel (< 0: taken over, never handed off again)
+  unsigned short list_a[kWavePool];   // rays to scan (unordered)
+  unsigned short list_b[kWavePool];   // the same rays sorted by kind
+  unsigned short free_list[kWavePool];
+  unsigned char kind[kWavePool];
+  int counts[8];
+  int cursor[8];
+  int n_next;      // length of list_a being built
+  int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
+  int free_count;
+  int pixel_dry;   // the pixel queue has run dry
+};
+
+PT_DEV int material_of(const SceneDesc& sc, int id) {
+  const int idx = id & (int)kIdMask;
+  switch (id >> kIdShift) {
+    case G_SPHERE: return sc.sphere_aux[idx].material;
+    case G_MOVING_SPHERE: return sc.moving_aux[idx].material;
+    case G_RECT: return sc.rect_aux[idx].material;
+    case G_TRIANGLE: return sc.tri_aux[idx].material;
+    case G_BOX: return sc.box_aux[idx].material;
+    default: return sc.media[idx].material;
+  }
+}
+
+PT_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+
+// Queue position -> pixel of the region.  Consecutive positions are spread over the image (a
+// multiplicative permutation), so every CTA traces a representative mix of cheap and deep pixels.
+PT_DEV void queue_pixel(const RenderParams& p, unsigned long long n_pixels, unsigned long long pos, int& px, int& py,
+                        float*& out_px) {
+  const unsigned long long i = (pos * p.scramble) % n_pixels;
+  const unsigned long long k = i / (unsigned long long)p.region.w, xx = i - k * (unsigned long long)p.region.w;
+  px = p.region.x0 + (int)xx;
+  py = p.region.y0 + (int)k * p.region.y_stride;
+  out_px = p.out + (long long)k * p.out_row_pitch + 3ll * (long long)xx;
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const RenderParams p) {
+  extern __shared__ __align__(16) unsigned char smem_blob[];
+  __shared__ __align__(8) uint64_t stage_bar;
+
+  const SceneDesc& sc = p.scene;
+  const unsigned char* blob_base = sc.blob;
+  const uint32_t pool_offset = kSmem ? ((sc.blob_bytes + 127u) & ~127u) : 0u;
+  if constexpr (kSmem) {
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&stage_bar, sc.blob_bytes);
+      constexpr uint32_t kPiece = 32768;
+      for (uint32_t off = 0; off < sc.blob_bytes; off += kPiece)
+        bulk_g2s(smem_blob + off, sc.blob + off, min(kPiece, sc.blob_bytes - off), &stage_bar);
+    }
+    mbar_wait(&stage_bar, 0);
+    blob_base = smem_blob;
+  }
+  WavePool& W = *reinterpret_cast<WavePool*>(smem_blob + pool_offset);
+  SceneView sv;
+  sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
+  sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
+  sv.moving = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
+  sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
+  sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
+  sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
+
+  if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const pt_camera& cam = p.cam;
+  const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
+  const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
+  const unsigned lane_lt = (1u << lane) - 1u;
+  const HeavyQueue& hq = p.heavy;
+  const bool express = (int)blockIdx.x < p.n_express;  // this CTA only serves the hand-off queue
+  const int own_cap = express ? 0 : p.pool_cap;
+  unsigned int n_scans = 0;
+
+  // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
+  auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py) -> bool {
+    if (W.pixel_dry) return false;
+    const unsigned long long pos = atomicAdd(p.pixel_counter, 1ull);
+    if (pos >= n_pixels) {
+      W.pixel_dry = 1;
+      if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+      return false;
+    }
+    pixq = (uint32_t)pos;
+    float* unused;
+    queue_pixel(p, n_pixels, pos, px, py, unused);
+    // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+    rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+    return true;
+  };
+  // Append the live slots of this warp to the next scan list (one shared-memory atomic per warp).
+  auto append = [&](bool alive, bool own, int slot) {
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    const unsigned mo = __ballot_sync(0xffffffffu, alive && own);
+    if (m != 0u) {
+      int base = 0;
+      if (lane == 0) {
+        base = atomicAdd(&W.n_next, __popc(m));
+        if (mo != 0u) atomicAdd(&W.n_own, __popc(mo));
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (alive) W.list_a[base + __popc(m & lane_lt)] = (unsigned short)slot;
+    }
+  };
+  auto store_ray = [&](int slot, const Ray& ray, V3 att, V3 acc, Rng rng, int bounce, int sample) {
+    W.ox[slot] = ray.o.x, W.oy[slot] = ray.o.y, W.oz[slot] = ray.o.z;
+    W.dx[slot] = ray.d.x, W.dy[slot] = ray.d.y, W.dz[slot] = ray.d.z, W.tm[slot] = ray.tm;
+    W.att_x[slot] = att.x, W.att_y[slot] = att.y, W.att_z[slot] = att.z;
+    W.acc_x[slot] = acc.x, W.acc_y[slot] = acc.y, W.acc_z[slot] = acc.z;
+    W.rng[slot] = rng.s, W.bounce[slot] = bounce, W.sample[slot] = sample;
+  };
+
+  // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
+  if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
+  if (tid == 0) W.n_next = 0, W.n_own = 0, W.free_count = 0, W.pixel_dry = 0;
+  __syncthreads();
+  for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
+    const int slot = s0 + lane;
+    bool alive = false;
+    if (slot < own_cap) {
+      uint32_t pixq;
+      Rng rng;
+      int px, py;
+      if (next_pixel(pixq, rng, px, py)) {
+        Ray ray;
+        camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+        store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+        W.pix[slot] = pixq, W.scans[slot] = 0;
+        alive = true;
+      }
+    }
+    if (!alive) W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;
+    append(alive, true, slot);
+  }
+  __syncthreads();
+
+  bool reported_done = false;
+  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
+  for (;;) {
+    int n = W.n_next;  // rays carried over from the last round
+    // ---- a CTA that can no longer produce hand-offs says so (once)
+    if (!reported_done && (express || (W.pixel_dry && W.n_own == 0))) {
+      reported_done = true;
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(hq.ctrl + 2, 1u);
+        if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
+      }
+    }
+    // ---- INTAKE from the hand-off queue: express CTAs always, the others once their own pixels ran out
+    if ((express || W.pixel_dry) && n < kExpressCap) {
+      bool got = false;
+      int slot = 0;
+      if (tid < kExpressCap - n) {
+        unsigned int h = ld_volatile_u32(hq.ctrl + 0);
+        for (int attempt = 0; attempt < 4 && !got; ++attempt) {
+          const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
+          if (h >= t) break;
+          const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
+          if (seen == h) got = true; else h = seen;
+        }
+        if (got) {
+          while (ld_volatile_u32(hq.ready + h) != hq.stamp && globaltimer_ns() <= t_give_up) __nanosleep(100);
+          __threadfence();
+          const float* e = hq.entries + (size_t)h * kHeavyEntryWords;
+          slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
+          Ray ray;
+          ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
+          ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
+          ray.tm = __ldcg(e + 10);
+          store_ray(slot, ray, v3(__ldcg(e + 11), __ldcg(e + 12), __ldcg(e + 13)),
+                    v3(__ldcg(e + 14), __ldcg(e + 15), __ldcg(e + 16)), Rng { __float_as_uint(__ldcg(e + 1)) },
+                    __float_as_int(__ldcg(e + 3)), __float_as_int(__ldcg(e + 2)));
+          W.pix[slot] = __float_as_uint(__ldcg(e + 0));
+          W.scans[slot] = -1;  // taken over: never handed off again
+        }
+      }
+      append(got, false, slot);
+      __syncthreads();
+      n = W.n_next;
+    }
+    if (n == 0) {
+      // nothing to trace: finished when every producer is done and the queue is empty, else wait for hand-offs
+      const bool all_done = ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
+                            ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
+      const bool timed_out = globaltimer_ns() > t_give_up;
+      if (timed_out && p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
+      if (__syncthreads_or((all_done || timed_out) ? 1 : 0)) break;
+      __nanosleep(1000);
+      continue;
+    }
+
+    // ---- SCAN: choose lanes per ray so that the CTA's lanes are used best
+    int team_size = 1, passes = (n + kWaveThreads - 1) / kWaveThreads;
+    {
+      float best_cost = (float)passes * 1.0f;
+      for (int t = 2, lg = 1; t <= 32; t <<= 1, ++lg) {
+        const int ps = (n * t + kWaveThreads - 1) / kWaveThreads;
+        const float cost = (float)ps * (1.5f / (float)t + 0.03f * (float)lg);  // measured: strided team scans cost more per test
+        if (cost < best_cost) best_cost = cost, team_size = t, passes = ps;
+      }
+    }
+    const int member = tid & (team_size - 1);
+    const int rays_per_pass = kWaveThreads / team_size;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int entry = pass * rays_per_pass + tid / team_size;
+      const bool act = entry < n;
+      const int slot = act ? (int)W.list_a[entry] : 0;
+      Ray ray;
+      ray.o = v3(W.ox[slot], W.oy[slot], W.oz[slot]);
+      ray.d = v3(W.dx[slot], W.dy[slot], W.dz[slot]);
+      ray.tm = W.tm[slot];
+      Rng rng { W.rng[slot] };
+      if (!act) ray.d = v3(0.f, 0.f, 0.f);
+      const Best best = closest_hit<kSmem>(sc, sv, ray, rng, act, member, team_size);
+      if (act && member == 0) {
+        W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
+        W.rng[slot] = rng.s;  // a constant_medium may have drawn from it (constant_medium.hpp:65)
+        if (W.scans[slot] >= 0) W.scans[slot] += 1;
+        int kind = 0;
+        if (best.id >= 0) kind = 1 + reinterpret_cast<const pt_material*>(sc.materials)[material_of(sc, best.id)].kind;
+        W.kind[slot] = (unsigned char)kind;
+        atomicAdd(&W.counts[kind], 1);
+        ++n_scans;
+      }
+    }
+    __syncthreads();
+
+    // ---- SORT by kind (counting sort; the order inside a kind does not matter)
+    {
+      int base[kWaveKinds];
+      int run = 0;
+#pragma unroll
+      for (int k = 0; k < kWaveKinds; ++k) base[k] = run, run += W.counts[k];
+      for (int e = tid; e < n; e += kWaveThreads) {
+        const int slot = (int)W.list_a[e];
+        const int k = (int)W.kind[slot];
+        int b = 0;
+#pragma unroll
+        for (int q = 0; q < kWaveKinds; ++q)
+          if (q == k) b = base[q];
+        W.list_b[b + atomicAdd(&W.cursor[k], 1)] = (unsigned short)slot;
+      }
+      if (tid == 0) W.n_next = 0, W.n_own = 0;
+    }
+    __syncthreads();
+
+    // ---- SHADE: one warp per batch of 32 consecutive sorted rays
+    if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
+    const int heavy_rate = W.pixel_dry ? kHeavyRateDry : kHeavyRate;
+    for (int e0 = warp * 32; e0 < n; e0 += kWaveThreads) {
+      const int e = e0 + lane;
+      const bool act = e < n;
+      const int slot = act ? (int)W.list_b[e] : 0;
+      bool alive = false, own = false;
+      if (act) {
+        Ray ray;
+        ray.o = v3(W.ox[slot], W.oy[slot], W.oz[slot]);
+        ray.d = v3(W.dx[slot], W.dy[slot], W.dz[slot]);
+        ray.tm = W.tm[slot];
+        const Best best { W.hit_t[slot], W.hit_id[slot] };
+        V3 att = v3(W.att_x[slot], W.att_y[slot], W.att_z[slot]);
+        V3 acc = v3(W.acc_x[slot], W.acc_y[slot], W.acc_z[slot]);
+        Rng rng { W.rng[slot] };
+        int bounce = W.bounce[slot], sample = W.sample[slot];
+        uint32_t pixq = W.pix[slot];
+        const int scans = W.scans[slot];
+        own = scans >= 0;
+        V3 contribution;
+        bool new_pixel = false;
+        alive = true;
+        if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
+          // the path ended: render.hpp:100-105
+          acc = vadd(acc, contribution);
+          int px, py;
+          float* out_px;
+          queue_pixel(p, n_pixels, pixq, px, py, out_px);
+          if (++sample == p.spp) {
+            const V3 fin = vdivs(acc, fspp);
+            out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+            new_pixel = true;
+          } else {
+            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            att = v3(1.f, 1.f, 1.f);
+            bounce = 0;
+          }
+        }
+        // a heavy pixel leaves for a CTA that runs short rounds, with its complete state
+        if (!new_pixel && own && scans > kHeavyBase + heavy_rate * sample && ld_volatile_u32(hq.ctrl + 1) < hq.cap) {
+          const unsigned int i = atomicAdd(hq.ctrl + 1, 1u);
+          if (i < hq.cap) {
+            float* q = hq.entries + (size_t)i * kHeavyEntryWords;
+            __stcg(q + 0, __uint_as_float(pixq)), __stcg(q + 1, __uint_as_float(rng.s));
+            __stcg(q + 2, __int_as_float(sample)), __stcg(q + 3, __int_as_float(bounce));
+            __stcg(q + 4, ray.o.x), __stcg(q + 5, ray.o.y), __stcg(q + 6, ray.o.z);
+            __stcg(q + 7, ray.d.x), __stcg(q + 8, ray.d.y), __stcg(q + 9, ray.d.z), __stcg(q + 10, ray.tm);
+            __stcg(q + 11, att.x), __stcg(q + 12, att.y), __stcg(q + 13, att.z);
+            __stcg(q + 14, acc.x), __stcg(q + 15, acc.y), __stcg(q + 16, acc.z);
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int*>(hq.ready + i) = hq.stamp;
+            new_pixel = true;
+          }
+        }
+        if (new_pixel) {
+          int px, py;
+          alive = !express && next_pixel(pixq, rng, px, py);
+          if (alive) {
+            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            att = v3(1.f, 1.f, 1.f);
+            acc = v3(0.f, 0.f, 0.f);
+            bounce = 0, sample = 0;
+            W.pix[slot] = pixq, W.scans[slot] = 0;
+            own = true;
+          } else {
+            W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;
+          }
+        }
+        if (alive) store_ray(slot, ray, att, acc, rng, bounce, sample);
+      }
+      append(alive, own, slot);
+    }
+    __syncthreads();
+  }
+
+  if (p.counters && lane == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
+  unsigned int warp_scans = n_scans;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_scans += __shfl_xor_sync(0xffffffffu, warp_scans, o);
+  if (lane == 0 && p.counters) atomicAdd(p.counters, (unsigned long long)warp_scans);
+}
+
 // ---------------------------------------------------------------- launch
 int max_smem_blob_bytes(int device) {
   int optin = 0;
@@ -926,6 +1196,47 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
   int sms = 0;
   cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
+  RenderParams q = p;
+  const unsigned long long pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
+  if (p.kernel_kind == 0) {
+    // ---- wavefront kernel: one CTA per SM, ray pool + (when it fits) the scan blob in shared memory
+    const size_t pool_bytes = sizeof(WavePool);
+    const size_t staged_bytes = ((size_t)p.scene.blob_bytes + 127u) / 128u * 128u + pool_bytes;
+    const bool smem = (long long)staged_bytes <= (long long)max_smem_blob_bytes(device);
+    const size_t dyn = smem ? staged_bytes : pool_bytes;
+    auto kernel = smem ? render_wave_kernel<true> : render_wave_kernel<false>;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (err != cudaSuccess) return err;
+    // every CTA must be resident at once: the express warps wait for all CTAs to report
+    int resident = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kWaveThreads, dyn);
+    if (err != cudaSuccess) return err;
+    if (resident < 1) return cudaErrorLaunchOutOfResources;
+    int grid = grid_override > 0 ? grid_override : sms;
+    if (grid > sms * resident) grid = sms * resident;
+    const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
+    q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
+    // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
+    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 15) / 24 : 0);
+    if (q.n_express >= grid) q.n_express = grid - 1;
+    // pixel-order permutation pos -> (pos * scramble) mod pixels: a multiplier near pixels / golden ratio,
+    // made coprime with the pixel count so that it is a bijection
+    unsigned long long mul = (unsigned long long)((double)pixels * 0.6180339887498949) | 1ull;
+    auto gcd = [](unsigned long long a, unsigned long long b) {
+      while (b) {
+        const unsigned long long t = a % b;
+        a = b, b = t;
+      }
+      return a;
+    };
+    while (pixels > 1 && gcd(mul % pixels, pixels) != 1ull) mul += 2ull;
+    q.scramble = pixels > 1 ? mul % pixels : 1ull;
+    if (q.scramble == 0ull) q.scramble = 1ull;
+    if (info) info->grid = grid, info->block = kWaveThreads, info->smem_bytes = (int)dyn, info->blocks_per_sm = 1, info->staged = smem, info->team_size = 0;
+    kernel<<<grid, kWaveThreads, dyn, stream>>>(q);
+    return cudaGetLastError();
+  }
+  // ---- lane kernel: a pixel per lane team, state in registers
   const bool smem = (int)p.scene.blob_bytes <= max_smem_blob_bytes(device);
   const size_t dyn = smem ? p.scene.blob_bytes : 0;
   auto kernel = smem ? render_kernel<true> : render_kernel<false>;
@@ -939,8 +1250,16 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
   if (per_sm < 1) per_sm = 1;
   if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
   int grid = grid_override > 0 ? grid_override : sms * per_sm;
-  if (info) info->grid = grid, info->block = kBlockThreads, info->smem_bytes = (int)dyn, info->blocks_per_sm = per_sm, info->staged = smem;
-  kernel<<<grid, kBlockThreads, dyn, stream>>>(p);
+  // Lanes per pixel at launch: one in the normal case; with fewer than kMinPixelsPerTeam pixels per
+  // team (a small region, or an image strongly scaled over many GPUs) the teams start larger.
+  if (q.team_size <= 0) {
+    const unsigned long long lanes = (unsigned long long)grid * kBlockThreads;
+    int t = 1;
+    while (t < 32 && pixels * (unsigned long long)t * 2ull < lanes * (unsigned long long)kMinPixelsPerTeam) t <<= 1;
+    q.team_size = t;
+  }
+  if (info) info->grid = grid, info->block = kBlockThreads, info->smem_bytes = (int)dyn, info->blocks_per_sm = per_sm, info->staged = smem, info->team_size = q.team_size;
+  kernel<<<grid, kBlockThreads, dyn, stream>>>(q);
   return cudaGetLastError();
 }
 

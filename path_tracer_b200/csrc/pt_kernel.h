@@ -19,6 +19,18 @@ constexpr int kBlockThreads = PT_BLOCK_THREADS;
 constexpr int kMinBlocksPerSM = PT_MIN_BLOCKS_PER_SM;
 constexpr int kMaxBlocksPerSM = PT_MIN_BLOCKS_PER_SM;  // persistent grid = SMs x this
 
+// Global hand-off queue for HEAVY pixels (wavefront kernel): bounded, written once per entry per
+// launch, consumed by the express warps of every CTA.  ctrl[0] = head, ctrl[1] = tail, ctrl[2] = CTAs
+// whose regular work is finished.
+constexpr int kHeavyEntryWords = 20;
+struct HeavyQueue {
+  unsigned int* ctrl;
+  unsigned int* ready;   // ready[i] == stamp once entry i is fully written
+  float* entries;        // kHeavyEntryWords words per entry
+  unsigned int cap;
+  unsigned int stamp;    // changes every launch, so `ready` never needs clearing
+};
+
 struct RenderParams {
   SceneDesc scene;
   pt_camera cam;
@@ -28,10 +40,16 @@ struct RenderParams {
   long long out_row_pitch;  // floats
   unsigned long long* pixel_counter;  // work-queue head, zeroed before launch
   unsigned long long* counters;       // [0] += closest-hit scans (may be null)
+  int team_size;                      // lane kernel: lanes per pixel at launch (power of two, 1..32; 0 = automatic)
+  int kernel_kind;                    // 0 = wavefront kernel (default), 1 = lane kernel
+  int pool_cap;                       // wavefront kernel: pixels a CTA may hold (set by the launcher)
+  int n_express;                      // wavefront kernel: CTAs that only serve the hand-off queue (< 0 = automatic)
+  unsigned long long scramble;        // pixel-order multiplier (coprime with the pixel count), set by the launcher
+  HeavyQueue heavy;
 };
 
 struct LaunchInfo {
-  int grid, block, smem_bytes, blocks_per_sm;
+  int grid, block, smem_bytes, blocks_per_sm, team_size;
   bool staged;  // scan blob staged in shared memory (else streamed from L2)
 };
 

@@ -109,6 +109,49 @@ def test_c1_partition_invariance_and_determinism(c1):
     assert np.array_equal(_bits(R.render_region(sc, cam, w, h, spp, d, tile)), _bits(full[77:167, 123:323]))
 
 
+@pytest.mark.parametrize("name", ["media", "ties", "shapes", "moving"])
+def test_team_size_invariance(cport, name):
+    """Lanes-per-pixel (team size) is a scheduling choice: every power of two gives the same bits."""
+    sc, cam = scenes.ALL[name](64 / 48)
+    L = R.lib()
+    try:
+        base = None
+        for t in (1, 2, 4, 8, 16, 32):
+            L.pt_debug_set_team_size(t)
+            img = R.render(sc, cam, 64, 48, 6, 50)
+            if base is None:
+                base = img
+                want, cnt = cport.render(sc, cam, 64, 48, 6, 50)
+                assert_parity(img, want, (name, t))
+                assert R.stats()["scans"] == cnt.scans
+            else:
+                assert np.array_equal(_bits(img), _bits(base)), (name, t)
+    finally:
+        L.pt_debug_set_team_size(0)
+
+
+@pytest.mark.parametrize("name", ["media", "shapes", "moving", "c1"])
+def test_lane_kernel_equals_wavefront_kernel(name):
+    """The two schedulers (wavefront = default, lane = pixel-per-lane-team) share the device functions and
+    must produce the same bits."""
+    if name == "c1":
+        sc, cam, _ = scenes.load_c1()
+        w, h, spp = 160, 96, 8
+    else:
+        sc, cam = scenes.ALL[name](64 / 48)
+        w, h, spp = 64, 48, 6
+    L = R.lib()
+    wave = R.render(sc, cam, w, h, spp, 50)
+    wave_scans = R.stats()["scans"]
+    try:
+        L.pt_debug_set_kernel(1)
+        lane_img = R.render(sc, cam, w, h, spp, 50)
+        assert R.stats()["scans"] == wave_scans
+    finally:
+        L.pt_debug_set_kernel(0)
+    assert np.array_equal(_bits(wave), _bits(lane_img))
+
+
 def test_rtiow_config2_layout(cport):
     """BASELINE config 2 layout (about 480 static spheres) at reduced image size, full depth."""
     sc, cam = scenes.rtiow(16 / 9)
