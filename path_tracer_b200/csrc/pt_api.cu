@@ -23,6 +23,7 @@ namespace {
 thread_local std::string g_error;
 int g_num_gpus = 1;
 int g_team_size_override = 0;
+int g_lpt_enabled = 1;  // pt_debug_set_lpt
 int g_n_express = -1;   // < 0: automatic (pt_debug_set_express)
 int g_kernel_kind = 0;  // 0 = wavefront kernel, 1 = lane kernel (pt_debug_set_kernel)
 pt_stats g_stats {};
@@ -62,7 +63,10 @@ struct pt_device_scene {
   unsigned int* heavy_ready = nullptr;
   float* heavy_entries = nullptr;
   unsigned int launch_stamp = 0;
+  int* lpt_buf = nullptr;  // probe costs + tile order + scratch of the LPT pixel ordering
+  size_t lpt_ints = 0;
   int next_slot = 0;
+  unsigned int kernel_launches = 0;  // kernels launched since creation (probe, tile sort, render)
   unsigned long long paths_launched = 0;
   LaunchInfo last_launch {};
 };
@@ -241,6 +245,7 @@ void pt_scene_free(pt_device_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   cudaFree(s->arena);
+  if (s->lpt_buf) cudaFree(s->lpt_buf);
   delete s;
 }
 
@@ -266,25 +271,64 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   p.region = *region;
   p.out = d_out;
   p.out_row_pitch = out_row_pitch;
-  const int slot = scene->next_slot;
-  scene->next_slot = (slot + 1) % kCounterSlots;
-  p.pixel_counter = scene->queue_heads + slot;
   p.counters = scene->counters;
   p.team_size = g_team_size_override;  // 0 = chosen from the pixel count at launch
   p.kernel_kind = g_kernel_kind;
   p.pool_cap = 0;
   p.scramble = 1;
   p.n_express = g_n_express;
+  p.order_mode = 0, p.tile_order = nullptr, p.tiles_x = p.tiles_y = 0, p.probe_cost = nullptr, p.n_positions = 0;
   p.heavy.ctrl = scene->heavy_ctrl, p.heavy.ready = scene->heavy_ready, p.heavy.entries = scene->heavy_entries;
-  p.heavy.cap = kHeavyCap, p.heavy.stamp = ++scene->launch_stamp;
-  PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
-  PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, sizeof(unsigned long long), st));
+  p.heavy.cap = kHeavyCap;
+  auto next_queue_head = [&]() {
+    const int slot = scene->next_slot;
+    scene->next_slot = (slot + 1) % kCounterSlots;
+    return scene->queue_heads + slot;
+  };
   PT_CUDA(cudaMemsetAsync(p.counters + 1, 0xff, 2 * sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 3, 0, 2 * sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 5, 0xff, sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 6, 0, sizeof(unsigned long long), st));
+
+  // Longest-processing-time-first pixel order (wavefront kernel, images worth it): a cost probe traces
+  // ONE throw-away sample through every second pixel of every second row (1/(4 spp) of the frame's
+  // work), the tiles are sorted by probed cost, and the frame starts with the most expensive tiles so
+  // that the deepest pixels have the whole frame to finish and the cheapest ones fill its end.
+  const unsigned long long pixels = (unsigned long long)region->w * (unsigned long long)region->h;
+  if (g_lpt_enabled && pixels >= 32768ull && spp >= 8) {
+    const int pw = (region->w + kProbeStep - 1) / kProbeStep, ph = (region->h + kProbeStep - 1) / kProbeStep;
+    const int tiles_x = (region->w + kTile - 1) / kTile, tiles_y = (region->h + kTile - 1) / kTile;
+    const size_t need = (size_t)pw * ph + 2 * (size_t)tiles_x * tiles_y;
+    if (need > scene->lpt_ints) {
+      if (scene->lpt_buf) cudaFree(scene->lpt_buf);
+      scene->lpt_buf = nullptr, scene->lpt_ints = 0;
+      PT_CUDA(cudaMalloc(&scene->lpt_buf, need * sizeof(int)));
+      scene->lpt_ints = need;
+    }
+    int* probe_cost = scene->lpt_buf;
+    int* tile_order = probe_cost + (size_t)pw * ph;
+    int* scratch = tile_order + (size_t)tiles_x * tiles_y;
+    RenderParams probe = p;
+    probe.order_mode = 2, probe.probe_cost = probe_cost, probe.spp = 1, probe.counters = nullptr;
+    probe.kernel_kind = 0;  // the probe always runs on the wavefront kernel
+    probe.pixel_counter = next_queue_head();
+    probe.heavy.stamp = ++scene->launch_stamp;
+    PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
+    PT_CUDA(cudaMemsetAsync(probe.pixel_counter, 0, sizeof(unsigned long long), st));
+    cudaError_t pe = launch_render(probe, scene->device, 0, st, nullptr);
+    if (pe != cudaSuccess) return cuda_fail(pe, "cost probe launch");
+    pe = launch_tile_order(probe_cost, region->w, region->h, tiles_x, tiles_y, tile_order, scratch, st);
+    if (pe != cudaSuccess) return cuda_fail(pe, "tile order launch");
+    p.order_mode = 1, p.tile_order = tile_order, p.tiles_x = tiles_x, p.tiles_y = tiles_y;
+    scene->kernel_launches += 2;
+  }
+  p.pixel_counter = next_queue_head();
+  p.heavy.stamp = ++scene->launch_stamp;
+  PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
+  PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, sizeof(unsigned long long), st));
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
+  scene->kernel_launches += 1;
   scene->paths_launched += (unsigned long long)region->w * region->h * spp;
   return PT_OK;
 }
@@ -315,6 +359,12 @@ int pt_debug_set_team_size(int t) {
 // Debug aid (not part of pt_abi.h): 0 = wavefront kernel (default), 1 = lane kernel.
 int pt_debug_set_kernel(int kind) {
   g_kernel_kind = kind;
+  return PT_OK;
+}
+
+// Debug aid (not part of pt_abi.h): switch the LPT pixel ordering (cost probe + tile sort) on / off.
+int pt_debug_set_lpt(int on) {
+  g_lpt_enabled = on;
   return PT_OK;
 }
 
@@ -377,7 +427,7 @@ int pt_render_region(int width, int height, int spp, int depth, const pt_camera*
     cudaEventElapsedTime(&ms, ev[2], ev[3]);
     st.d2h_ms = ms;
     st.d2h_bytes = row_floats * region->h * sizeof(float);
-    st.kernel_launches = depth > 0 ? 1 : 0;
+    st.kernel_launches = ds->kernel_launches;
     uint64_t paths = 0, scans = 0;
     pt_scene_read_counters(ds, &paths, &scans, 0);
     st.paths = (uint64_t)region->w * region->h * spp, st.scans = scans;
@@ -484,7 +534,7 @@ int pt_render(int width, int height, int spp, int depth, const pt_camera* camera
     st.d2h_ms = ms, st.d2h_bytes = row_floats * height * sizeof(float);
     cudaEventDestroy(a), cudaEventDestroy(b);
     st.paths = (uint64_t)width * height * spp;
-    st.kernel_launches = depth > 0 ? (uint32_t)n : 0;
+    for (int d = 0; d < n; ++d) st.kernel_launches += scenes[d]->kernel_launches;
     g_stats = st;
   }
   cleanup();

@@ -46,10 +46,17 @@ constexpr float kTMin = 0.001f;  // render.hpp:40
 #define PT_SCAN_UNROLL 4
 #endif
 constexpr int kScanUnroll = PT_SCAN_UNROLL;  // spheres per hot-loop trip
+#ifndef PT_DEEP_RATE
+#define PT_DEEP_RATE 20
+#endif
+constexpr int kDeepRate = PT_DEEP_RATE;  // lane kernel: a pixel is DEEP above kDeepBase + kDeepRate * samples scans so far
+constexpr int kDeepBase = 64;
 #ifndef PT_MIN_PIXELS_PER_TEAM
 #define PT_MIN_PIXELS_PER_TEAM 3
 #endif
 constexpr int kMinPixelsPerTeam = PT_MIN_PIXELS_PER_TEAM;  // launch with larger teams below this many pixels per team
+
+PT_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
 
 PT_DEV unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -111,13 +118,33 @@ struct Best {
   int id;
 };
 
+// Tie-break keys of every object (pt_packed.h); small enough to travel by value into out-of-line code.
+struct KeyTable {
+  const int32_t* keys;
+  uint32_t base[6];
+};
+PT_DEV KeyTable key_table(const SceneDesc& sc) {
+  KeyTable k;
+  k.keys = sc.keys;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) k.base[i] = sc.key_base[i];
+  return k;
+}
+PT_DEV int key_of(const KeyTable& kt, int id) {
+  const int type = id >> kIdShift;
+  uint32_t b = kt.base[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (type == i) b = kt.base[i];
+  return kt.keys[b + (uint32_t)(id & (int)kIdMask)];
+}
 PT_DEV int key_of(const SceneDesc& sc, int id) {
   return sc.keys[sc.key_base[id >> kIdShift] + (uint32_t)(id & (int)kIdMask)];
 }
 
 // Winner rule: minimum t, then maximum key (pt_packed.h).  Called with a
 // candidate that already satisfies its own primitive's range test.
-PT_DEV void consider(const SceneDesc& sc, Best& best, float t, int id) {
+template <typename Keys> PT_DEV void consider(const Keys& sc, Best& best, float t, int id) {
   if (t < best.t) {
     best.t = t, best.id = id;
   } else if (t == best.t) {
@@ -126,7 +153,7 @@ PT_DEV void consider(const SceneDesc& sc, Best& best, float t, int id) {
 }
 // rect / triangle / box accept with `!(t > max)`, which lets NaN through
 // (rectangle.hpp:36, triangle.hpp:91): mirror that.
-PT_DEV void consider_le(const SceneDesc& sc, Best& best, float t, int id) {
+template <typename Keys> PT_DEV void consider_le(const Keys& sc, Best& best, float t, int id) {
   if (t == best.t) {
     if (best.id < 0 || key_of(sc, id) > key_of(sc, best.id)) best.id = id;
   } else {
@@ -137,8 +164,9 @@ PT_DEV void consider_le(const SceneDesc& sc, Best& best, float t, int id) {
 // ---------------------------------------------------------------- primitives
 // Exact roots of one sphere for the scan (sphere.hpp:74-105 with max = +inf;
 // the running-closest filter is applied by consider()).  `a` = dot(d,d).
-PT_DEV void sphere_roots_scan(const SceneDesc& sc, Best& best, const Ray& r, float a, float cx, float cy,
-                              float cz, float r2, int id) {
+template <typename Keys>
+PT_DEV void sphere_roots_scan(const Keys& sc, Best& best, const Ray& r, float a, float cx, float cy, float cz, float r2,
+                              int id) {
   const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
   const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
   const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
@@ -297,68 +325,86 @@ PT_DEV void team_merge(const SceneDesc& sc, Best& best, int team_size) {
 // phase 2 computes exact roots for the set bits.  The stride-1 instance is the steady-state hot
 // loop (4 spheres per trip so that it stays inside the instruction cache).
 template <bool kSmem, bool kMoving>
-PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, int first, int end, int stride,
-                         const Ray& r, float a, float f, bool act, int type, Best& best) {
-  auto center = [&](int i, float& cx, float& cy, float& cz, float& r2) {
-    if constexpr (kMoving) {
-      const float4 s = ld4<kSmem>(data + 2 * i);
-      const float4 v = ld4<kSmem>(data + 2 * i + 1);
-      cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2 = s.w;  // sphere.hpp:55
-    } else {
-      const float4 s = ld4<kSmem>(data + i);
-      cx = s.x, cy = s.y, cz = s.z, r2 = s.w;
-    }
-  };
-  auto positive = [&](int i) {
-    float cx, cy, cz, r2;
-    center(i, cx, cy, cz, r2);
-    const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
-    const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-    const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
-    return fsub(fmul(b, b), fmul(a, c)) > 0.f;
-  };
-  if (stride == 1) {
-    // group sizes are padded to kSphereChunk with spheres that can never be hit (pt_pack.cpp)
-#pragma unroll 1
-    for (int base = first; base < end; base += kSphereChunk) {
-      uint32_t mask = 0;
-#pragma unroll 1
-      for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
-        uint32_t nib = 0;
-#pragma unroll
-        for (int j = 0; j < kScanUnroll; ++j)
-          if (positive(base + it + j)) nib |= (1u << j);
-        mask |= nib << it;
-      }
-      if (!act) mask = 0;
-      while (mask) {
-        const int j = __ffs(mask) - 1;
-        mask &= mask - 1;
-        float cx, cy, cz, r2;
-        center(base + j, cx, cy, cz, r2);
-        sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, base + j));
-      }
-    }
+PT_DEV void sphere_center(const float4* __restrict__ data, int i, float f, float& cx, float& cy, float& cz, float& r2) {
+  if constexpr (kMoving) {
+    const float4 s = ld4<kSmem>(data + 2 * i);
+    const float4 v = ld4<kSmem>(data + 2 * i + 1);
+    cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2 = s.w;  // sphere.hpp:55
   } else {
+    const float4 s = ld4<kSmem>(data + i);
+    cx = s.x, cy = s.y, cz = s.z, r2 = s.w;
+  }
+}
+template <bool kSmem, bool kMoving>
+PT_DEV bool sphere_positive(const float4* __restrict__ data, int i, float f, const Ray& r, float a) {
+  float cx, cy, cz, r2;
+  sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2);
+  const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
+  const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
+  const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
+  return fsub(fmul(b, b), fmul(a, c)) > 0.f;
+}
+
+// The steady-state hot loop (stride 1): 4 spheres per trip so that it stays inside the instruction cache;
+// group sizes are padded to kSphereChunk with spheres that can never be hit (pt_pack.cpp).
+template <bool kSmem, bool kMoving>
+PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ data, int first, int end, const Ray& r,
+                              float a, float f, bool act, int type, Best& best) {
 #pragma unroll 1
-    for (int base = first; base < end; base += kSphereChunk * stride) {
-      uint32_t mask = 0;
-#pragma unroll 2
-      for (int it = 0; it < kSphereChunk; ++it) {
-        const int i = base + it * stride;
-        if (i < end && positive(i)) mask |= (1u << it);
-      }
-      if (!act) mask = 0;
-      while (mask) {
-        const int it = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int i = base + it * stride;
-        float cx, cy, cz, r2;
-        center(i, cx, cy, cz, r2);
-        sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, i));
-      }
+  for (int base = first; base < end; base += kSphereChunk) {
+    uint32_t mask = 0;
+#pragma unroll 1
+    for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
+      uint32_t nib = 0;
+#pragma unroll
+      for (int j = 0; j < kScanUnroll; ++j)
+        if (sphere_positive<kSmem, kMoving>(data, base + it + j, f, r, a)) nib |= (1u << j);
+      mask |= nib << it;
+    }
+    if (!act) mask = 0;
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      float cx, cy, cz, r2;
+      sphere_center<kSmem, kMoving>(data, base + j, f, cx, cy, cz, r2);
+      sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, base + j));
     }
   }
+}
+
+// The team variant (member m takes elements first, first+stride, ...): out of line and by value, so
+// that it does not sit between the hot loops in the instruction stream.
+template <bool kSmem, bool kMoving>
+__device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __restrict__ data, int first, int end,
+                                                  int stride, Ray r, float a, float f, bool act, int type, Best best) {
+  const int n_it = (end - first + stride - 1) / stride;  // elements of this member
+#pragma unroll 1
+  for (int it0 = 0; it0 < n_it; it0 += kSphereChunk) {
+    uint32_t mask = 0;
+    const int lim = min(kSphereChunk, n_it - it0);
+#pragma unroll 2
+    for (int it = 0; it < lim; ++it)
+      if (sphere_positive<kSmem, kMoving>(data, first + (it0 + it) * stride, f, r, a)) mask |= (1u << it);
+    if (!act) mask = 0;
+    while (mask) {
+      const int it = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int i = first + (it0 + it) * stride;
+      float cx, cy, cz, r2;
+      sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2);
+      sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, i));
+    }
+  }
+  return best;
+}
+
+template <bool kSmem, bool kMoving>
+PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, int first, int end, int stride,
+                         const Ray& r, float a, float f, bool act, int type, Best& best) {
+  if (stride == 1)
+    scan_spheres_unit<kSmem, kMoving>(sc, data, first, end, r, a, f, act, type, best);
+  else
+    best = scan_spheres_strided<kSmem, kMoving>(key_table(sc), data, first, end, stride, r, a, f, act, type, best);
 }
 
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
@@ -642,6 +688,213 @@ PT_DEV bool shade(const SceneDesc& sc, const SceneView& sv, int depth, bool smem
   return bounce == depth;  // render.hpp:91: out of depth -> black
 }
 
+// Queue position -> pixel of the region (false: the position falls outside the region and is skipped).
+//   order_mode 1  tiles sorted by probed cost, heaviest first (longest-processing-time-first: the
+//                 deep pixels of the image start at once, the cheapest ones fill the end of the frame)
+//   order_mode 0  consecutive positions spread over the image by a multiplicative permutation
+//   order_mode 2  the cost probe itself: every kProbeStep-th pixel of every kProbeStep-th row
+PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, int& py, float*& out_px) {
+  unsigned long long k, xx;
+  if (p.order_mode == 1) {
+    const int tile = p.tile_order[pos / (unsigned long long)(kTile * kTile)];
+    const int i = (int)(pos % (unsigned long long)(kTile * kTile));
+    xx = (unsigned long long)((tile % p.tiles_x) * kTile + (i % kTile));
+    k = (unsigned long long)((tile / p.tiles_x) * kTile + (i / kTile));
+    if (xx >= (unsigned long long)p.region.w || k >= (unsigned long long)p.region.h) return false;
+  } else if (p.order_mode == 2) {
+    const unsigned long long pw = (unsigned long long)((p.region.w + kProbeStep - 1) / kProbeStep);
+    xx = (pos % pw) * kProbeStep, k = (pos / pw) * kProbeStep;
+  } else {
+    const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
+    const unsigned long long i = (pos * p.scramble) % n_pixels;
+    k = i / (unsigned long long)p.region.w, xx = i - k * (unsigned long long)p.region.w;
+  }
+  px = p.region.x0 + (int)xx;
+  py = p.region.y0 + (int)k * p.region.y_stride;
+  out_px = p.out + (long long)k * p.out_row_pitch + 3ll * (long long)xx;
+  return true;
+}
+
+// ---------------------------------------------------------------- the lane loop
+// One warp, k = 32 / team_size pixels at a time, the path state of each pixel replicated in the
+// registers of its team (see the header comment).  kExpress = false: pixels come from the pixel queue
+// (the lane kernel).  kExpress = true: complete path states come from the hand-off queue of the
+// wavefront kernel and are traced to their last sample (the express service).
+template <bool kSmem, bool kExpress>
+PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneView& sv, int team_size0,
+                      unsigned int& n_scans) {
+  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
+  const pt_camera& cam = p.cam;
+  const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
+  const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
+
+  // per-lane path state, replicated across the lanes of a team
+  const int lane = (int)(threadIdx.x & 31u);
+  int team_size = team_size0;         // lanes per pixel (power of two); grows when the warp is re-packed
+  int member = lane & (team_size - 1);
+  bool live = false;                  // owns a pixel
+  bool need_path = true;              // must start a new camera sample
+  bool exhausted_queue = false;       // the pixel queue has run dry
+  int px = 0, py = 0;                 // global pixel coordinates
+  float* out_px = nullptr;
+  int sample = p.spp;
+  int bounce = 0;
+  Rng rng { 0u };
+  Ray ray { v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), 0.f };
+  V3 att = v3(1.f, 1.f, 1.f);
+  V3 acc = v3(0.f, 0.f, 0.f);
+  int pix_scans = 0;  // closest-hit scans spent on the current pixel
+
+  for (;;) {
+    // ---- (R) re-pack: the queue is dry for this warp and at most half of its teams still own a
+    // pixel -> move the survivors into teams twice (or more) as large.
+    if (team_size < 32) {
+      const unsigned can_fetch = __ballot_sync(0xffffffffu, !live && !exhausted_queue);
+      const unsigned leaders = __ballot_sync(0xffffffffu, live && member == 0);
+      const int k_live = __popc(leaders);
+      if (can_fetch == 0u && k_live > 0 && 2 * k_live * team_size <= 32) {
+        int new_size = team_size;
+        while (2 * k_live * new_size <= 32) new_size <<= 1;
+        const int new_team = lane / new_size;
+        const bool keep = new_team < k_live;
+        const int src = keep ? (int)__fns(leaders, 0u, new_team + 1) : lane;  // leader lane of the new_team-th live team
+#define PT_MOVE(x) x = __shfl_sync(0xffffffffu, x, src)
+        PT_MOVE(px), PT_MOVE(py), PT_MOVE(sample), PT_MOVE(bounce), PT_MOVE(rng.s), PT_MOVE(pix_scans);
+        PT_MOVE(ray.o.x), PT_MOVE(ray.o.y), PT_MOVE(ray.o.z), PT_MOVE(ray.d.x), PT_MOVE(ray.d.y), PT_MOVE(ray.d.z);
+        PT_MOVE(ray.tm), PT_MOVE(att.x), PT_MOVE(att.y), PT_MOVE(att.z), PT_MOVE(acc.x), PT_MOVE(acc.y), PT_MOVE(acc.z);
+        unsigned long long optr = (unsigned long long)out_px;
+        PT_MOVE(optr);
+        out_px = (float*)optr;
+        int np = need_path ? 1 : 0;
+        PT_MOVE(np);
+        need_path = np != 0;
+#undef PT_MOVE
+        live = keep;
+        exhausted_queue = true;
+        team_size = new_size;
+        member = lane & (team_size - 1);
+      }
+    }
+
+    // ---- (A) path regeneration: render.hpp:94-105 sample loop, :130-133 seeding
+    if (need_path && live && sample == p.spp) {
+      // final_color /= samples; fb[y][x] = final_color (render.hpp:102-105); one writer per team
+      const V3 fin = vdivs(acc, fspp);
+      if (member == 0) out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+      live = false;
+    }
+    {
+      const bool wants = need_path && !live && !exhausted_queue;
+      if (__any_sync(0xffffffffu, wants)) {
+        if constexpr (!kExpress) {
+          unsigned long long idx = 0ull;
+          if (wants && member == 0) {  // the team leader pulls the next pixel (skipping tile positions outside the region)
+            int tx, ty;
+            float* tp;
+            do idx = atomicAdd(p.pixel_counter, 1ull);
+            while (idx < p.n_positions && !queue_pixel(p, idx, tx, ty, tp));
+          }
+          idx = __shfl_sync(0xffffffffu, idx, lane - member);
+          if (wants) {
+            if (idx < p.n_positions) {
+              queue_pixel(p, idx, px, py, out_px);
+              // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+              rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+              acc = v3(0.f, 0.f, 0.f);
+              sample = 0;
+              pix_scans = 0;
+              live = true;
+            } else {
+              exhausted_queue = true;
+              if (p.counters && member == 0) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+            }
+          }
+        } else {
+          // express service: the team leader takes a handed-off pixel (complete path state) from the global queue
+          const HeavyQueue& hq = p.heavy;
+          int j = -1;  // -1: nothing now, -2: never again
+          if (wants && member == 0) {
+            unsigned int h = ld_volatile_u32(hq.ctrl + 0);
+            for (int attempt = 0; attempt < 8; ++attempt) {
+              const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
+              if (h >= t) {
+                if (ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
+                    ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap))
+                  j = -2;  // every producer is done and the queue is empty
+                break;
+              }
+              const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
+              if (seen == h) {
+                j = (int)h;
+                break;
+              }
+              h = seen;
+            }
+            if (j >= 0) {
+              while (ld_volatile_u32(hq.ready + j) != hq.stamp && globaltimer_ns() <= t_give_up) __nanosleep(100);
+              __threadfence();
+            }
+            if (globaltimer_ns() > t_give_up) {
+              if (p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
+              j = -2;
+            }
+          }
+          j = __shfl_sync(0xffffffffu, j, lane - member);
+          if (wants) {
+            if (j >= 0) {
+              const float* e = hq.entries + (size_t)j * kHeavyEntryWords;
+              queue_pixel(p, (unsigned long long)__float_as_uint(__ldcg(e + 0)), px, py, out_px);
+              rng.s = __float_as_uint(__ldcg(e + 1));
+              sample = __float_as_int(__ldcg(e + 2)), bounce = __float_as_int(__ldcg(e + 3));
+              ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
+              ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
+              ray.tm = __ldcg(e + 10);
+              att = v3(__ldcg(e + 11), __ldcg(e + 12), __ldcg(e + 13));
+              acc = v3(__ldcg(e + 14), __ldcg(e + 15), __ldcg(e + 16));
+              pix_scans = 0;
+              live = true;
+              need_path = false;  // the pixel continues in the middle of a path
+            } else if (j == -2) {
+              exhausted_queue = true;
+            }
+          }
+        }
+      }
+    }
+    if (need_path && live) {
+      camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+      att = v3(1.f, 1.f, 1.f);
+      bounce = 0;
+      need_path = false;
+    }
+    if (!__any_sync(0xffffffffu, live)) {
+      if (__all_sync(0xffffffffu, exhausted_queue)) break;
+      __nanosleep(300);  // express service: wait for hand-offs
+      continue;
+    }
+
+    // ---- (B) closest hit: render.hpp:60 -> :30-51
+    const Best best = closest_hit<kSmem>(sc, sv, ray, rng, live, member, team_size);
+
+    // ---- (C) shade: render.hpp:58-91 (every member of a team computes the same thing)
+    if (live) {
+      if (member == 0) ++n_scans;
+      ++pix_scans;
+      V3 contribution;
+      if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
+        acc = vadd(acc, contribution);
+        ++sample;
+        need_path = true;
+      }
+    }
+    // A warp that finds itself holding one of the image's deepest pixels stops taking new pixels: as its
+    // other pixels finish it is re-packed into ever larger teams, until all 32 lanes scan for the deep
+    // pixel and its remaining thousands of bounces take microseconds each instead of a full round.
+    if (!kExpress && __any_sync(0xffffffffu, live && pix_scans > kDeepBase + kDeepRate * sample)) exhausted_queue = true;
+  }
+
+}
+
 // ---------------------------------------------------------------- the kernel
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(const RenderParams p) {
@@ -675,112 +928,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
-  const pt_camera& cam = p.cam;
-  const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
-  const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
-
-  // per-lane path state, replicated across the lanes of a team
-  const int lane = (int)(threadIdx.x & 31u);
-  int team_size = p.team_size;        // lanes per pixel (power of two); grows when the warp is re-packed
-  int member = lane & (team_size - 1);
-  bool live = false;                  // owns a pixel
-  bool need_path = true;              // must start a new camera sample
-  bool exhausted_queue = false;       // the pixel queue has run dry
-  int px = 0, py = 0;                 // global pixel coordinates
-  float* out_px = nullptr;
-  int sample = p.spp;
-  int bounce = 0;
-  Rng rng { 0u };
-  Ray ray { v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), 0.f };
-  V3 att = v3(1.f, 1.f, 1.f);
-  V3 acc = v3(0.f, 0.f, 0.f);
   unsigned int n_scans = 0;
-
-  for (;;) {
-    // ---- (R) re-pack: the queue is dry for this warp and at most half of its teams still own a
-    // pixel -> move the survivors into teams twice (or more) as large.
-    if (team_size < 32) {
-      const unsigned can_fetch = __ballot_sync(0xffffffffu, !live && !exhausted_queue);
-      const unsigned leaders = __ballot_sync(0xffffffffu, live && member == 0);
-      const int k_live = __popc(leaders);
-      if (can_fetch == 0u && k_live > 0 && 2 * k_live * team_size <= 32) {
-        int new_size = team_size;
-        while (2 * k_live * new_size <= 32) new_size <<= 1;
-        const int new_team = lane / new_size;
-        const bool keep = new_team < k_live;
-        const int src = keep ? (int)__fns(leaders, 0u, new_team + 1) : lane;  // leader lane of the new_team-th live team
-#define PT_MOVE(x) x = __shfl_sync(0xffffffffu, x, src)
-        PT_MOVE(px), PT_MOVE(py), PT_MOVE(sample), PT_MOVE(bounce), PT_MOVE(rng.s);
-        PT_MOVE(ray.o.x), PT_MOVE(ray.o.y), PT_MOVE(ray.o.z), PT_MOVE(ray.d.x), PT_MOVE(ray.d.y), PT_MOVE(ray.d.z);
-        PT_MOVE(ray.tm), PT_MOVE(att.x), PT_MOVE(att.y), PT_MOVE(att.z), PT_MOVE(acc.x), PT_MOVE(acc.y), PT_MOVE(acc.z);
-        unsigned long long optr = (unsigned long long)out_px;
-        PT_MOVE(optr);
-        out_px = (float*)optr;
-        int np = need_path ? 1 : 0;
-        PT_MOVE(np);
-        need_path = np != 0;
-#undef PT_MOVE
-        live = keep;
-        exhausted_queue = true;
-        team_size = new_size;
-        member = lane & (team_size - 1);
-      }
-    }
-
-    // ---- (A) path regeneration: render.hpp:94-105 sample loop, :130-133 seeding
-    if (need_path && live && sample == p.spp) {
-      // final_color /= samples; fb[y][x] = final_color (render.hpp:102-105); one writer per team
-      const V3 fin = vdivs(acc, fspp);
-      if (member == 0) out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
-      live = false;
-    }
-    {
-      const bool wants = need_path && !live && !exhausted_queue;
-      if (__any_sync(0xffffffffu, wants)) {
-        unsigned long long idx = 0ull;
-        if (wants && member == 0) idx = atomicAdd(p.pixel_counter, 1ull);  // the team leader pulls the next pixel
-        idx = __shfl_sync(0xffffffffu, idx, lane - member);
-        if (wants) {
-          if (idx < n_pixels) {
-            const int k = (int)(idx / (unsigned long long)p.region.w);
-            const int xx = (int)(idx - (unsigned long long)k * (unsigned long long)p.region.w);
-            px = p.region.x0 + xx;
-            py = p.region.y0 + k * p.region.y_stride;
-            out_px = p.out + (long long)k * p.out_row_pitch + 3ll * xx;
-            // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
-            rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
-            acc = v3(0.f, 0.f, 0.f);
-            sample = 0;
-            live = true;
-          } else {
-            exhausted_queue = true;
-            if (p.counters && member == 0) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
-          }
-        }
-      }
-    }
-    if (need_path && live) {
-      camera_ray(cam, px, py, fwidth, fheight, rng, ray);
-      att = v3(1.f, 1.f, 1.f);
-      bounce = 0;
-      need_path = false;
-    }
-    if (!__any_sync(0xffffffffu, live)) break;
-
-    // ---- (B) closest hit: render.hpp:60 -> :30-51
-    const Best best = closest_hit<kSmem>(sc, sv, ray, rng, live, member, team_size);
-
-    // ---- (C) shade: render.hpp:58-91 (every member of a team computes the same thing)
-    if (live) {
-      if (member == 0) ++n_scans;
-      V3 contribution;
-      if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
-        acc = vadd(acc, contribution);
-        ++sample;
-        need_path = true;
-      }
-    }
-  }
+  lane_loop<kSmem, false>(p, sc, sv, p.team_size, n_scans);
 
   if (p.counters && (threadIdx.x & 31) == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   // work counters: one atomic per warp
@@ -826,10 +975,10 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 #define PT_HEAVY_RATE 10
 #endif
 #ifndef PT_HEAVY_RATE_DRY
-#define PT_HEAVY_RATE_DRY 4
+#define PT_HEAVY_RATE_DRY 10
 #endif
-#ifndef PT_EXPRESS_CAP
-#define PT_EXPRESS_CAP 64
+#ifndef PT_EXPRESS_TEAM
+#define PT_EXPRESS_TEAM 16
 #endif
 constexpr int kWaveThreads = PT_WAVE_THREADS;
 constexpr int kWavePool = PT_WAVE_ROUNDS * kWaveThreads;  // pixels (rays) a CTA keeps in flight: whole scan passes
@@ -837,7 +986,7 @@ constexpr int kWaveKinds = 6;                              // 0 = background, 1 
 constexpr int kHeavyRate = PT_HEAVY_RATE;                  // heavy: more than kHeavyBase + rate * samples scans so far
 constexpr int kHeavyRateDry = PT_HEAVY_RATE_DRY;           // ... a lower bar once the pixel queue is dry (load sharing)
 constexpr int kHeavyBase = 64;
-constexpr int kExpressCap = PT_EXPRESS_CAP;                // rays in flight in a CTA that serves the hand-off queue
+constexpr int kExpressTeam = PT_EXPRESS_TEAM;              // lanes per handed-off pixel in the express service
 
 struct WavePool {
   float ox[kWavePool], oy[kWavePool], oz[kWavePool], dx[kWavePool], dy[kWavePool], dz[kWavePool], tm[kWavePool];
@@ -860,6 +1009,9 @@ struct WavePool {
   int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
   int free_count;
   int pixel_dry;   // the pixel queue has run dry
+  // per-round snapshot of the global queues, taken by thread 0 so that every thread decides alike
+  unsigned int snap_head, snap_tail, snap_done, snap_timeout;
+  unsigned long long snap_consumed;
 };
 
 PT_DEV int material_of(const SceneDesc& sc, int id) {
@@ -872,19 +1024,6 @@ PT_DEV int material_of(const SceneDesc& sc, int id) {
     case G_BOX: return sc.box_aux[idx].material;
     default: return sc.media[idx].material;
   }
-}
-
-PT_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
-
-// Queue position -> pixel of the region.  Consecutive positions are spread over the image (a
-// multiplicative permutation), so every CTA traces a representative mix of cheap and deep pixels.
-PT_DEV void queue_pixel(const RenderParams& p, unsigned long long n_pixels, unsigned long long pos, int& px, int& py,
-                        float*& out_px) {
-  const unsigned long long i = (pos * p.scramble) % n_pixels;
-  const unsigned long long k = i / (unsigned long long)p.region.w, xx = i - k * (unsigned long long)p.region.w;
-  px = p.region.x0 + (int)xx;
-  py = p.region.y0 + (int)k * p.region.y_stride;
-  out_px = p.out + (long long)k * p.out_row_pitch + 3ll * (long long)xx;
 }
 
 template <bool kSmem>
@@ -919,29 +1058,31 @@ __global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const Rend
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const pt_camera& cam = p.cam;
-  const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
   const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
   const unsigned lane_lt = (1u << lane) - 1u;
   const HeavyQueue& hq = p.heavy;
   const bool express = (int)blockIdx.x < p.n_express;  // this CTA only serves the hand-off queue
-  const int own_cap = express ? 0 : p.pool_cap;
+  const int own_cap = p.pool_cap;
   unsigned int n_scans = 0;
 
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
   auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py) -> bool {
-    if (W.pixel_dry) return false;
-    const unsigned long long pos = atomicAdd(p.pixel_counter, 1ull);
-    if (pos >= n_pixels) {
-      W.pixel_dry = 1;
-      if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
-      return false;
+    for (;;) {
+      if (W.pixel_dry) return false;
+      const unsigned long long pos = atomicAdd(p.pixel_counter, 1ull);
+      if (pos >= p.n_positions) {
+        W.pixel_dry = 1;
+        if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+        return false;
+      }
+      float* unused;
+      if (!queue_pixel(p, pos, px, py, unused)) continue;  // a tile position outside the region
+      pixq = (uint32_t)pos;
+      // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+      rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+      if (p.order_mode == 2) rng.s = (rng.s * 2654435761u) | 1u;  // cost probe: a throw-away stream, never the pixel's
+      return true;
     }
-    pixq = (uint32_t)pos;
-    float* unused;
-    queue_pixel(p, n_pixels, pos, px, py, unused);
-    // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
-    rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
-    return true;
   };
   // Append the live slots of this warp to the next scan list (one shared-memory atomic per warp).
   auto append = [&](bool alive, bool own, int slot) {
@@ -965,6 +1106,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const Rend
     W.rng[slot] = rng.s, W.bounce[slot] = bounce, W.sample[slot] = sample;
   };
 
+  if (!express) {
   // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
   if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
   if (tid == 0) W.n_next = 0, W.n_own = 0, W.free_count = 0, W.pixel_dry = 0;
@@ -989,61 +1131,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const Rend
   }
   __syncthreads();
 
-  bool reported_done = false;
-  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
+  // ---- rounds of SCAN / SORT / SHADE until this CTA's own pixels are finished
   for (;;) {
-    int n = W.n_next;  // rays carried over from the last round
-    // ---- a CTA that can no longer produce hand-offs says so (once)
-    if (!reported_done && (express || (W.pixel_dry && W.n_own == 0))) {
-      reported_done = true;
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(hq.ctrl + 2, 1u);
-        if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
-      }
-    }
-    // ---- INTAKE from the hand-off queue: express CTAs always, the others once their own pixels ran out
-    if ((express || W.pixel_dry) && n < kExpressCap) {
-      bool got = false;
-      int slot = 0;
-      if (tid < kExpressCap - n) {
-        unsigned int h = ld_volatile_u32(hq.ctrl + 0);
-        for (int attempt = 0; attempt < 4 && !got; ++attempt) {
-          const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
-          if (h >= t) break;
-          const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
-          if (seen == h) got = true; else h = seen;
-        }
-        if (got) {
-          while (ld_volatile_u32(hq.ready + h) != hq.stamp && globaltimer_ns() <= t_give_up) __nanosleep(100);
-          __threadfence();
-          const float* e = hq.entries + (size_t)h * kHeavyEntryWords;
-          slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
-          Ray ray;
-          ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
-          ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
-          ray.tm = __ldcg(e + 10);
-          store_ray(slot, ray, v3(__ldcg(e + 11), __ldcg(e + 12), __ldcg(e + 13)),
-                    v3(__ldcg(e + 14), __ldcg(e + 15), __ldcg(e + 16)), Rng { __float_as_uint(__ldcg(e + 1)) },
-                    __float_as_int(__ldcg(e + 3)), __float_as_int(__ldcg(e + 2)));
-          W.pix[slot] = __float_as_uint(__ldcg(e + 0));
-          W.scans[slot] = -1;  // taken over: never handed off again
-        }
-      }
-      append(got, false, slot);
-      __syncthreads();
-      n = W.n_next;
-    }
-    if (n == 0) {
-      // nothing to trace: finished when every producer is done and the queue is empty, else wait for hand-offs
-      const bool all_done = ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
-                            ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
-      const bool timed_out = globaltimer_ns() > t_give_up;
-      if (timed_out && p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
-      if (__syncthreads_or((all_done || timed_out) ? 1 : 0)) break;
-      __nanosleep(1000);
-      continue;
-    }
+    const int n = W.n_next;  // rays to trace this round
+    if (n == 0) break;
 
     // ---- SCAN: choose lanes per ray so that the CTA's lanes are used best
     int team_size = 1, passes = (n + kWaveThreads - 1) / kWaveThreads;
@@ -1129,10 +1220,14 @@ __global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const Rend
           acc = vadd(acc, contribution);
           int px, py;
           float* out_px;
-          queue_pixel(p, n_pixels, pixq, px, py, out_px);
+          queue_pixel(p, pixq, px, py, out_px);
           if (++sample == p.spp) {
-            const V3 fin = vdivs(acc, fspp);
-            out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+            if (p.order_mode == 2) {
+              p.probe_cost[pixq] = scans;  // cost probe: how deep did one sample of this pixel go
+            } else {
+              const V3 fin = vdivs(acc, fspp);
+              out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+            }
             new_pixel = true;
           } else {
             camera_ray(cam, px, py, fwidth, fheight, rng, ray);
@@ -1141,7 +1236,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const Rend
           }
         }
         // a heavy pixel leaves for a CTA that runs short rounds, with its complete state
-        if (!new_pixel && own && scans > kHeavyBase + heavy_rate * sample && ld_volatile_u32(hq.ctrl + 1) < hq.cap) {
+        if (!new_pixel && own && p.order_mode != 2 && scans > kHeavyBase + heavy_rate * sample &&
+            ld_volatile_u32(hq.ctrl + 1) < hq.cap) {
           const unsigned int i = atomicAdd(hq.ctrl + 1, 1u);
           if (i < hq.cap) {
             float* q = hq.entries + (size_t)i * kHeavyEntryWords;
@@ -1176,12 +1272,61 @@ __global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const Rend
     }
     __syncthreads();
   }
+  }  // regular CTA
+
+  // ---- no regular work (left): say so, then serve the hand-off queue until the whole GPU is finished
+  if (tid == 0) {
+    __threadfence();
+    atomicAdd(hq.ctrl + 2, 1u);
+    if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
+  }
+  lane_loop<kSmem, true>(p, sc, sv, kExpressTeam, n_scans);
 
   if (p.counters && lane == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   unsigned int warp_scans = n_scans;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) warp_scans += __shfl_xor_sync(0xffffffffu, warp_scans, o);
   if (lane == 0 && p.counters) atomicAdd(p.counters, (unsigned long long)warp_scans);
+}
+
+// ---------------------------------------------------------------- LPT tile order
+// One block: bin the tiles by probed cost (sum of the probes inside the tile), then list them from the
+// most expensive bin to the cheapest (counting sort; the order inside a bin does not matter).
+constexpr int kCostBins = 1024;
+__global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict__ probe_cost, int region_w, int region_h,
+                                                           int tiles_x, int tiles_y, int* __restrict__ tile_order,
+                                                           int* __restrict__ tile_bin) {
+  __shared__ int hist[kCostBins];
+  __shared__ int start[kCostBins];
+  const int n_tiles = tiles_x * tiles_y;
+  const int pw = (region_w + kProbeStep - 1) / kProbeStep, ph = (region_h + kProbeStep - 1) / kProbeStep;
+  for (int b = threadIdx.x; b < kCostBins; b += blockDim.x) hist[b] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    const int tx = t % tiles_x, ty = t / tiles_x;
+    int cost = 0;
+    for (int j = 0; j < kTile / kProbeStep; ++j)
+      for (int i = 0; i < kTile / kProbeStep; ++i) {
+        const int qx = tx * (kTile / kProbeStep) + i, qy = ty * (kTile / kProbeStep) + j;
+        if (qx < pw && qy < ph) cost += probe_cost[qy * pw + qx];
+      }
+    const int bin = min(cost, kCostBins - 1);
+    tile_bin[t] = bin;
+    atomicAdd(&hist[bin], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = kCostBins - 1; b >= 0; --b) start[b] = run, run += hist[b];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) tile_order[atomicAdd(&start[tile_bin[t]], 1)] = t;
+}
+
+cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
+                              int* tile_order, int* scratch, cudaStream_t stream) {
+  tile_order_kernel<<<1, 1024, 0, stream>>>(probe_cost, region_w, region_h, tiles_x, tiles_y, tile_order, scratch);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- launch
@@ -1217,8 +1362,21 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
     // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
-    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 15) / 24 : 0);
+    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 9) / 18 : 0);  // 8 of 148: measured best on the default scene
     if (q.n_express >= grid) q.n_express = grid - 1;
+    if (p.order_mode == 2) {
+      q.n_express = 0;
+      q.n_positions = (unsigned long long)((p.region.w + kProbeStep - 1) / kProbeStep) *
+                      (unsigned long long)((p.region.h + kProbeStep - 1) / kProbeStep);
+    } else if (p.order_mode == 1) {
+      q.n_positions = (unsigned long long)p.tiles_x * (unsigned long long)p.tiles_y * (unsigned long long)(kTile * kTile);
+    } else {
+      q.n_positions = pixels;
+    }
+    {
+      const unsigned long long sh = (q.n_positions + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
+      q.pool_cap = (int)(sh < 32ull ? 32ull : (sh > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : sh));
+    }
     // pixel-order permutation pos -> (pos * scramble) mod pixels: a multiplier near pixels / golden ratio,
     // made coprime with the pixel count so that it is a bijection
     unsigned long long mul = (unsigned long long)((double)pixels * 0.6180339887498949) | 1ull;
@@ -1237,6 +1395,10 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     return cudaGetLastError();
   }
   // ---- lane kernel: a pixel per lane team, state in registers
+  if (p.order_mode == 1)
+    q.n_positions = (unsigned long long)p.tiles_x * (unsigned long long)p.tiles_y * (unsigned long long)(kTile * kTile);
+  else
+    q.n_positions = pixels, q.order_mode = 0, q.scramble = 1ull;  // row-major
   const bool smem = (int)p.scene.blob_bytes <= max_smem_blob_bytes(device);
   const size_t dyn = smem ? p.scene.blob_bytes : 0;
   auto kernel = smem ? render_kernel<true> : render_kernel<false>;

@@ -44,6 +44,12 @@ struct RenderParams {
   int kernel_kind;                    // 0 = wavefront kernel (default), 1 = lane kernel
   int pool_cap;                       // wavefront kernel: pixels a CTA may hold (set by the launcher)
   int n_express;                      // wavefront kernel: CTAs that only serve the hand-off queue (< 0 = automatic)
+  // pixel order of the wavefront kernel (queue position -> pixel)
+  int order_mode;                     // 0 = scrambled, 1 = tiles in `tile_order` (heaviest first), 2 = cost probe grid
+  const int* tile_order;              // order_mode 1: tile ids (kTile x kTile pixels) in processing order
+  int tiles_x, tiles_y;
+  int* probe_cost;                    // order_mode 2: scans of one throw-away sample per probed pixel
+  unsigned long long n_positions;     // queue length (set by the launcher)
   unsigned long long scramble;        // pixel-order multiplier (coprime with the pixel count), set by the launcher
   HeavyQueue heavy;
 };
@@ -52,6 +58,13 @@ struct LaunchInfo {
   int grid, block, smem_bytes, blocks_per_sm, team_size;
   bool staged;  // scan blob staged in shared memory (else streamed from L2)
 };
+
+constexpr int kTile = 8;   // LPT ordering granularity (pixels)
+constexpr int kProbeStep = 2;  // the cost probe traces every kProbeStep-th pixel of every kProbeStep-th row
+
+// Sort the region's tiles by probed cost, heaviest first (one small kernel).  `scratch` holds n_tiles ints.
+cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
+                              int* tile_order, int* scratch, cudaStream_t stream);
 
 int max_smem_blob_bytes(int device);
 cudaError_t launch_render(const RenderParams& p, int device, int grid_override, cudaStream_t stream,
