@@ -324,32 +324,53 @@ PT_DEV void team_merge(const SceneDesc& sc, Best& best, int team_size) {
 // Phase 1 is branch-free and only collects a bitmask of spheres whose discriminant is positive;
 // phase 2 computes exact roots for the set bits.  The stride-1 instance is the steady-state hot
 // loop (4 spheres per trip so that it stays inside the instruction cache).
+// Centre of sphere i at the ray's time (sphere.hpp:51-56), exactly as the reference computes it.
 template <bool kSmem, bool kMoving>
-PT_DEV void sphere_center(const float4* __restrict__ data, int i, float f, float& cx, float& cy, float& cz, float& r2) {
+PT_DEV void sphere_center(const float4* __restrict__ data, int i, float f, float& cx, float& cy, float& cz, float& r2_filter) {
   if constexpr (kMoving) {
     const float4 s = ld4<kSmem>(data + 2 * i);
     const float4 v = ld4<kSmem>(data + 2 * i + 1);
-    cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2 = s.w;  // sphere.hpp:55
+    cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2_filter = s.w;  // sphere.hpp:55
   } else {
     const float4 s = ld4<kSmem>(data + i);
-    cx = s.x, cy = s.y, cz = s.z, r2 = s.w;
+    cx = s.x, cy = s.y, cz = s.z, r2_filter = s.w;
   }
 }
+
+// CONSERVATIVE MISS FILTER (the hot instruction sequence of the whole renderer).  The reference
+// evaluates  disc = b*b - a*c,  b = dot(oc, d),  c = dot(oc, oc) - r*r  with 17 separately rounded
+// operations and hits only if disc > 0 (sphere.hpp:68-74).  Parity needs that exact sequence ONLY
+// for spheres that can be hit; for the other ~99 % it is enough to PROVE disc <= 0.  The filter
+// evaluates, with fused multiply-adds (11 operations),
+//     test = b'^2 - a(1-k) * (|oc|^2 - r^2 (1+e)),   e = 2k / (1-k)
+// which in exact arithmetic equals  disc + k * a * (|oc|^2 + r^2).  Either evaluation is within
+// 13 u a (|oc|^2 + r^2) of the exact real value (u = 2^-24; error analysis in DESIGN.md), so with
+// k = 4e-6 > 27 u the implication  (reference disc > 0)  =>  (test > 0)  always holds: the filter never
+// drops a sphere the reference would hit.  Spheres that pass are re-evaluated with the exact
+// sequence (sphere_roots_scan), so false positives only cost time.  The blob stores r^2 (1+e)
+// (rounded up); the exact r*r comes from the side table.
+constexpr float kFilterK = 4.0e-6f;
+PT_DEV float filter_a(float a) { return fmul(a, 1.0f - kFilterK); }
 template <bool kSmem, bool kMoving>
-PT_DEV bool sphere_positive(const float4* __restrict__ data, int i, float f, const Ray& r, float a) {
-  float cx, cy, cz, r2;
-  sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2);
+PT_DEV bool sphere_positive(const float4* __restrict__ data, int i, float f, const Ray& r, float a_filter) {
+  float cx, cy, cz, r2f;
+  sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
   const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
-  const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
-  const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
-  return fsub(fmul(b, b), fmul(a, c)) > 0.f;
+  const float b = __fmaf_rn(ocx, r.d.x, __fmaf_rn(ocy, r.d.y, fmul(ocz, r.d.z)));
+  const float c = __fmaf_rn(ocx, ocx, __fmaf_rn(ocy, ocy, __fmaf_rn(ocz, ocz, -r2f)));
+  return __fmaf_rn(b, b, -fmul(a_filter, c)) > 0.f;
+}
+PT_DEV float exact_r2(const SphereAux* aux, int i) {
+  const float radius = aux[i].radius;
+  return fmul(radius, radius);  // sphere.hpp:71
 }
 
 // The steady-state hot loop (stride 1): 4 spheres per trip so that it stays inside the instruction cache;
 // group sizes are padded to kSphereChunk with spheres that can never be hit (pt_pack.cpp).
 template <bool kSmem, bool kMoving>
-PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ data, int first, int end, const Ray& r,
-                              float a, float f, bool act, int type, Best& best) {
+PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ data, const SphereAux* aux, int first,
+                              int end, const Ray& r, float a, float f, bool act, int type, Best& best) {
+  const float af = filter_a(a);
 #pragma unroll 1
   for (int base = first; base < end; base += kSphereChunk) {
     uint32_t mask = 0;
@@ -358,16 +379,16 @@ PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ da
       uint32_t nib = 0;
 #pragma unroll
       for (int j = 0; j < kScanUnroll; ++j)
-        if (sphere_positive<kSmem, kMoving>(data, base + it + j, f, r, a)) nib |= (1u << j);
+        if (sphere_positive<kSmem, kMoving>(data, base + it + j, f, r, af)) nib |= (1u << j);
       mask |= nib << it;
     }
     if (!act) mask = 0;
     while (mask) {
       const int j = __ffs(mask) - 1;
       mask &= mask - 1;
-      float cx, cy, cz, r2;
-      sphere_center<kSmem, kMoving>(data, base + j, f, cx, cy, cz, r2);
-      sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, base + j));
+      float cx, cy, cz, r2f;
+      sphere_center<kSmem, kMoving>(data, base + j, f, cx, cy, cz, r2f);
+      sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, base + j), make_id(type, base + j));
     }
   }
 }
@@ -375,8 +396,10 @@ PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ da
 // The team variant (member m takes elements first, first+stride, ...): out of line and by value, so
 // that it does not sit between the hot loops in the instruction stream.
 template <bool kSmem, bool kMoving>
-__device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __restrict__ data, int first, int end,
-                                                  int stride, Ray r, float a, float f, bool act, int type, Best best) {
+__device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __restrict__ data, const SphereAux* aux,
+                                                  int first, int end, int stride, Ray r, float a, float f, bool act,
+                                                  int type, Best best) {
+  const float af = filter_a(a);
   const int n_it = (end - first + stride - 1) / stride;  // elements of this member
 #pragma unroll 1
   for (int it0 = 0; it0 < n_it; it0 += kSphereChunk) {
@@ -384,27 +407,27 @@ __device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __r
     const int lim = min(kSphereChunk, n_it - it0);
 #pragma unroll 2
     for (int it = 0; it < lim; ++it)
-      if (sphere_positive<kSmem, kMoving>(data, first + (it0 + it) * stride, f, r, a)) mask |= (1u << it);
+      if (sphere_positive<kSmem, kMoving>(data, first + (it0 + it) * stride, f, r, af)) mask |= (1u << it);
     if (!act) mask = 0;
     while (mask) {
       const int it = __ffs(mask) - 1;
       mask &= mask - 1;
       const int i = first + (it0 + it) * stride;
-      float cx, cy, cz, r2;
-      sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2);
-      sphere_roots_scan(sc, best, r, a, cx, cy, cz, r2, make_id(type, i));
+      float cx, cy, cz, r2f;
+      sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
+      sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
     }
   }
   return best;
 }
 
 template <bool kSmem, bool kMoving>
-PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, int first, int end, int stride,
-                         const Ray& r, float a, float f, bool act, int type, Best& best) {
+PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, const SphereAux* aux, int first, int end,
+                         int stride, const Ray& r, float a, float f, bool act, int type, Best& best) {
   if (stride == 1)
-    scan_spheres_unit<kSmem, kMoving>(sc, data, first, end, r, a, f, act, type, best);
+    scan_spheres_unit<kSmem, kMoving>(sc, data, aux, first, end, r, a, f, act, type, best);
   else
-    best = scan_spheres_strided<kSmem, kMoving>(key_table(sc), data, first, end, stride, r, a, f, act, type, best);
+    best = scan_spheres_strided<kSmem, kMoving>(key_table(sc), data, aux, first, end, stride, r, a, f, act, type, best);
 }
 
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
@@ -421,11 +444,11 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
     const int first = g.begin + member, end = g.begin + g.count;
     switch (g.type) {
       case G_SPHERE:
-        scan_spheres<kSmem, false>(sc, sv.sphere, first, end, team_size, r, a, 0.f, act, G_SPHERE, best);
+        scan_spheres<kSmem, false>(sc, sv.sphere, sc.sphere_aux, first, end, team_size, r, a, 0.f, act, G_SPHERE, best);
         break;
       case G_MOVING_SPHERE:
-        scan_spheres<kSmem, true>(sc, sv.moving, first, end, team_size, r, a, fdiv(fsub(r.tm, g.time0), g.den), act,
-                                  G_MOVING_SPHERE, best);
+        scan_spheres<kSmem, true>(sc, sv.moving, sc.moving_aux, first, end, team_size, r, a,
+                                  fdiv(fsub(r.tm, g.time0), g.den), act, G_MOVING_SPHERE, best);
         break;
       case G_RECT: {
         if (act)
@@ -966,10 +989,10 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 // Results are bit-identical to the lane kernel: the same device functions are called on the same
 // per-pixel state, only the assignment of work to lanes differs.
 #ifndef PT_WAVE_THREADS
-#define PT_WAVE_THREADS 512
+#define PT_WAVE_THREADS 896
 #endif
 #ifndef PT_WAVE_ROUNDS
-#define PT_WAVE_ROUNDS 2
+#define PT_WAVE_ROUNDS 1
 #endif
 #ifndef PT_HEAVY_RATE
 #define PT_HEAVY_RATE 10

@@ -167,7 +167,11 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
         const pt_sphere& s = sc.spheres[e.index];
         SphereAux a {};
         a.radius = s.radius, a.material = s.material, a.key = -1 - (int32_t)i;
-        const float r2 = s.radius * s.radius;
+        // The scan blob carries r*r inflated by the miss filter's margin, rounded up (pt_kernel.cu,
+        // "conservative miss filter"); the exact r*r is recomputed from the side table's radius.
+        const float r2_exact = s.radius * s.radius;
+        const float r2 = std::nextafter(r2_exact * (1.0f + 2.0f * 4.0e-6f / (1.0f - 4.0e-6f)),
+                                        std::numeric_limits<float>::infinity());
         if (s.time0 == s.time1) {  // sphere.hpp:52
           seg.sph.push_back(f4 { s.center0[0], s.center0[1], s.center0[2], r2 });
           seg.sph_aux.push_back(a);
