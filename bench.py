@@ -220,6 +220,7 @@ def main():
         rend.launch()
         rend.gather()
     rend.scene.counters(reset=True)
+    launches0 = rend.scene.launch_count()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -239,13 +240,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     paths_done, scans_done = rend.scene.counters()
-    t = torch.tensor([dev_ms, float(scans_done)], dtype=torch.float64, device=dev)
+    launches = rend.scene.launch_count() - launches0
+    t = torch.tensor([dev_ms, float(scans_done), float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, scans_total = float(tmax[0]), float(tsum[1])
+        dev_ms, scans_total, launches = float(tmax[0]), float(tsum[1]), int(tsum[2])
     else:
         scans_total = float(scans_done)
     ms_per_step = dev_ms / args.steps
@@ -315,7 +317,6 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
-    launches = args.steps * (1 if True else 0)
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -329,7 +330,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
-        "gpu_launches": launches * world,
+        "gpu_launches": int(launches),  # per step: cost probe + tile sort + render kernel, on every rank
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                      "frac": achieved / peak_tflops, "traffic": traffic, "flop_per_path": flop_per_path,
                      "peak_source": "FFMA micro-kernel measured in this run (%.0f MHz implied); MEASURED_PEAKS.json "

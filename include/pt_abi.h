@@ -251,6 +251,10 @@ int pt_render_region_device(const pt_device_scene* scene, int width, int height,
  * (paths, scans only; synchronises the device). */
 int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* scans, int reset);
 
+/* Kernels launched on this device scene since it was uploaded (a render is up to three: the cost
+ * probe, the tile sort and the render kernel itself). */
+int pt_scene_launch_count(const pt_device_scene* scene, uint64_t* launches);
+
 /* Peer framebuffer sharing between processes (one process per GPU): rank 0
  * allocates the framebuffer with pt_fb_alloc, exports a 64-byte handle, the
  * other ranks open it and pass the mapped pointer as d_out. */

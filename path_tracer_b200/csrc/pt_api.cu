@@ -124,11 +124,10 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   host.resize(o_heads + sizeof(unsigned long long) * (kCounterSlots + kCounterWords), 0);
   const size_t o_hctrl = align_up(host.size(), 256);
   host.resize(o_hctrl + 64, 0);
-  const size_t o_hready = align_up(host.size(), 256);
-  host.resize(o_hready + sizeof(unsigned) * kHeavyCap, 0);
   const size_t o_bytes = align_up(host.size(), 256);
   const size_t tex_bytes = std::max<size_t>((size_t)scene->n_texture_bytes, 3);
-  const size_t o_hentries = o_bytes + align_up(tex_bytes, 256);
+  const size_t o_hready = o_bytes + align_up(tex_bytes, 256);
+  const size_t o_hentries = o_hready + align_up(sizeof(unsigned) * kHeavyCap, 256);
   const size_t total = o_hentries + sizeof(float) * kHeavyEntryWords * (size_t)kHeavyCap;
 
   PT_CUDA(cudaSetDevice(device));
@@ -148,6 +147,7 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
     e = cudaMemcpyAsync(ds->arena + o_bytes, scene->texture_bytes, scene->n_texture_bytes, cudaMemcpyHostToDevice, 0);
   else if (e == cudaSuccess)
     e = cudaMemsetAsync(ds->arena + o_bytes, 0, 3, 0);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ds->arena + o_hready, 0, sizeof(unsigned) * kHeavyCap, 0);
   cudaEventRecord(ev1, 0);
   if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
   float ms = 0.f;
@@ -386,6 +386,12 @@ int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[5]) {
   out[0] = v[2] - v[1], out[1] = v[3] - v[1];
   out[2] = v[5] - v[1], out[3] = v[6] - v[1];  // first / last CTA out of regular work
   out[4] = ctrl[1];                            // heavy pixels handed to the express lane
+  return PT_OK;
+}
+
+int pt_scene_launch_count(const pt_device_scene* scene, uint64_t* launches) {
+  if (!scene || !launches) return fail(PT_ERR_INVALID_ARGUMENT, "pt_scene_launch_count: null argument");
+  *launches = scene->kernel_launches;
   return PT_OK;
 }
 

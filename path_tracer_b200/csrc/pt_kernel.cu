@@ -351,14 +351,16 @@ PT_DEV void sphere_center(const float4* __restrict__ data, int i, float f, float
 // (rounded up); the exact r*r comes from the side table.
 constexpr float kFilterK = 4.0e-6f;
 PT_DEV float filter_a(float a) { return fmul(a, 1.0f - kFilterK); }
+// Returns the bits of -test: the SIGN BIT is set for every sphere the filter lets through (and, harmlessly,
+// for -0 and some NaNs), so the per-lane candidate mask is collected with one funnel shift per sphere.
 template <bool kSmem, bool kMoving>
-PT_DEV bool sphere_positive(const float4* __restrict__ data, int i, float f, const Ray& r, float a_filter) {
+PT_DEV uint32_t sphere_filter_bits(const float4* __restrict__ data, int i, float f, const Ray& r, float a_filter) {
   float cx, cy, cz, r2f;
   sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
   const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
   const float b = __fmaf_rn(ocx, r.d.x, __fmaf_rn(ocy, r.d.y, fmul(ocz, r.d.z)));
   const float c = __fmaf_rn(ocx, ocx, __fmaf_rn(ocy, ocy, __fmaf_rn(ocz, ocz, -r2f)));
-  return __fmaf_rn(b, b, -fmul(a_filter, c)) > 0.f;
+  return __float_as_uint(__fmaf_rn(-b, b, fmul(a_filter, c)));
 }
 PT_DEV float exact_r2(const SphereAux* aux, int i) {
   const float radius = aux[i].radius;
@@ -373,19 +375,17 @@ PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ da
   const float af = filter_a(a);
 #pragma unroll 1
   for (int base = first; base < end; base += kSphereChunk) {
-    uint32_t mask = 0;
+    uint32_t mask = 0;  // sphere base + k ends up at bit 31 - k
 #pragma unroll 1
     for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
-      uint32_t nib = 0;
 #pragma unroll
       for (int j = 0; j < kScanUnroll; ++j)
-        if (sphere_positive<kSmem, kMoving>(data, base + it + j, f, r, af)) nib |= (1u << j);
-      mask |= nib << it;
+        mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, base + it + j, f, r, af), mask, 1);
     }
     if (!act) mask = 0;
     while (mask) {
-      const int j = __ffs(mask) - 1;
-      mask &= mask - 1;
+      const int j = __clz((int)mask);
+      mask &= ~(0x80000000u >> j);
       float cx, cy, cz, r2f;
       sphere_center<kSmem, kMoving>(data, base + j, f, cx, cy, cz, r2f);
       sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, base + j), make_id(type, base + j));
@@ -407,11 +407,12 @@ __device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __r
     const int lim = min(kSphereChunk, n_it - it0);
 #pragma unroll 2
     for (int it = 0; it < lim; ++it)
-      if (sphere_positive<kSmem, kMoving>(data, first + (it0 + it) * stride, f, r, af)) mask |= (1u << it);
+      mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, first + (it0 + it) * stride, f, r, af), mask, 1);
+    if (lim < kSphereChunk) mask <<= (kSphereChunk - lim);  // left-align: element it0 + k at bit 31 - k
     if (!act) mask = 0;
     while (mask) {
-      const int it = __ffs(mask) - 1;
-      mask &= mask - 1;
+      const int it = __clz((int)mask);
+      mask &= ~(0x80000000u >> it);
       const int i = first + (it0 + it) * stride;
       float cx, cy, cz, r2f;
       sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
@@ -991,6 +992,9 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 #ifndef PT_WAVE_THREADS
 #define PT_WAVE_THREADS 896
 #endif
+#ifndef PT_WAVE_BLOCKS_PER_SM
+#define PT_WAVE_BLOCKS_PER_SM 1
+#endif
 #ifndef PT_WAVE_ROUNDS
 #define PT_WAVE_ROUNDS 1
 #endif
@@ -1050,7 +1054,7 @@ PT_DEV int material_of(const SceneDesc& sc, int id) {
 }
 
 template <bool kSmem>
-__global__ void __launch_bounds__(kWaveThreads, 1) render_wave_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wave_kernel(const RenderParams p) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ __align__(8) uint64_t stage_bar;
 
@@ -1380,7 +1384,8 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kWaveThreads, dyn);
     if (err != cudaSuccess) return err;
     if (resident < 1) return cudaErrorLaunchOutOfResources;
-    int grid = grid_override > 0 ? grid_override : sms;
+    if (resident > PT_WAVE_BLOCKS_PER_SM) resident = PT_WAVE_BLOCKS_PER_SM;
+    int grid = grid_override > 0 ? grid_override : sms * resident;
     if (grid > sms * resident) grid = sms * resident;
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));

@@ -46,6 +46,7 @@ def lib():
         L.pt_scene_free.restype = None
         L.pt_render_region_device.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.pt_scene_read_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pt_scene_launch_count.argtypes = [C.c_void_p, C.c_void_p]
         L.pt_get_stats.argtypes = [C.c_void_p]
         L.pt_set_num_gpus.argtypes = [C.c_int]
         L.pt_fb_alloc.argtypes = [C.c_int, C.c_size_t, C.c_void_p]
@@ -126,6 +127,11 @@ class DeviceScene:
         _check(lib().pt_render_region_device(self._h, width, height, spp, depth, C.addressof(cam),
                                              C.addressof(region), C.c_void_p(d_out), out_row_pitch,
                                              C.c_void_p(stream)))
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(lib().pt_scene_launch_count(self._h, C.byref(n)))
+        return n.value
 
     def counters(self, reset=False):
         paths, scans = C.c_uint64(), C.c_uint64()
