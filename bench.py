@@ -9,8 +9,14 @@ src/main.cpp scene at 800x480, 100 spp, depth 50 (38.4 M paths; the scene and ca
 tests/golden/c1_scene.ptsc.gz, captured from the unmodified main.cpp).  A path = one camera sample.
 
   value   whole-job Mpaths/s with scene and framebuffer resident in HBM (device-resident C-ABI),
-          timed with CUDA events on the launching stream, max over ranks.  The image is fixed, so
-          N GPUs split the same rows (row r -> rank r mod N): scaling = "strong".
+          timed with CUDA events on the launching stream, max over ranks.
+  N > 1   the path shards by pixels with no data-path collective (seeds are global linear ids), so
+          the scaling run is WEAK: every GPU renders 480 rows.  N GPUs render the default scene with
+          the SAME camera at 800 x (480 N) -- N times the rows, interleaved (row r -> rank r mod N) --
+          and the rows land in rank 0's framebuffer through peer stores over NVLink (or an NCCL
+          gather).  At N = 1 this is exactly BASELINE config 1.  (Strong scaling of the fixed
+          384 000-pixel image is capped near 2x by its deepest pixel -- 3 151 serial bounces -- see
+          DESIGN.md section 7; `--scaling strong` measures it.)
   e2e     the same metric through the blocking host-buffer entry point (pt_render / the per-rank
           launcher): scene upload from pinned host memory + render + framebuffer download every step.
   roofline  FP32: achieved = value x W, W = algorithmic flop per path from the oracle's work counters
@@ -140,6 +146,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     sc, cam, w, h, spp, d = load_workload(args.workload)
+    # the reference's CPU path has one configuration (one box, its host cores): BASELINE config 1
     oracle = pick_cpu_oracle(w, h, spp, d)
     stride = args.cpu_stride
     for _ in range(args.warmup):
@@ -155,7 +162,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "reference default scene (fixture captured from the unmodified main.cpp); no external data",
         "config": {"workload": WORKLOADS[args.workload], "width": w, "height": h, "spp": spp, "depth": d},
         "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": oracle.kind,
@@ -178,6 +185,8 @@ def main():
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--cpu-stride", type=int, default=4, help="cpu baseline renders rows 0::stride")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 480 rows per GPU (image 800 x 480N), strong = the fixed 800x480 image")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -205,6 +214,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     sc, cam, w, h, spp, d = load_workload(args.workload)
+    if args.scaling == "weak":
+        h = h * world  # same scene and camera, N times the rows: every rank renders the base image's row count
     paths_per_step = w * h * spp
 
     def barrier():
@@ -269,14 +280,17 @@ def main():
             st = R.stats()
             h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
         else:
-            r2 = ptdist.DistRenderer(sc, cam, w, h, spp, d, rank, world, local_rank, mode=args.gather)
-            r2.launch()
-            full = r2.gather()
+            # per step: upload the scene to this rank's GPU, render its rows into the (persistent) shared
+            # framebuffer mapping / local rows, gather, and read the image back on rank 0
+            scene2 = R.DeviceScene(sc, local_rank)
+            ptr, pitch = rend.target()
+            scene2.render_region(cam, w, h, spp, d, rend.region, ptr, pitch, torch.cuda.current_stream().cuda_stream)
+            full = rend.gather()
             if rank == 0:
                 fb_host.copy_(full, non_blocking=False)
             h2d = int(sc.texture_bytes.size) + sum(int(a.nbytes) for a in sc.arrays().values())
             d2h = h * w * 12
-            r2.close()
+            scene2.close()
         barrier()
         if it >= args.warmup:
             e2e_times.append(time.perf_counter() - t0)
@@ -307,7 +321,7 @@ def main():
     # work counters for W: the C port counts them; a 1-in-16 row sample at full spp is plenty
     try:
         from oracle.pyoracle import CPort, rows_region
-        _, cnt = CPort().render_region(sc, cam, w, h, spp, d, rows_region(w, h, 0, 16))
+        _, cnt = CPort().render_region(sc, cam, w, h, spp, d, rows_region(w, h, 0, 16 * world))
         counters = cnt.as_dict()
         flop_per_path = flops_per_path(counters)
     except OSError:
@@ -319,10 +333,12 @@ def main():
         traffic = json.load(open(tpath)).get(args.workload)
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32",
         "data": "reference default scene (fixture captured from the unmodified main.cpp); no external data",
-        "config": {"workload": WORKLOADS[args.workload], "width": w, "height": h, "spp": spp, "depth": d,
+        "config": {"workload": WORKLOADS[args.workload] + ("" if world == 1 else
+                                                             "; %s scaling: image 800x%d over %d GPUs" % (args.scaling, h, world)),
+                   "width": w, "height": h, "spp": spp, "depth": d,
                    "paths_per_step": paths_per_step, "partition": "rows interleaved over %d rank(s)" % world,
                    "gather": args.gather if world > 1 else "none", "l2": "256 MiB memset between timed iterations",
                    "scans_per_path": scans_total / (paths_per_step * args.steps), "fb_mean": fb_check,
