@@ -73,6 +73,52 @@ struct pt_device_scene {
 
 namespace {
 
+// Device allocations are recycled across uploads (cudaMalloc / cudaFree cost milliseconds and
+// serialise the device; with peer mappings alive a cudaFree can take 100+ ms).  Only device memory is
+// kept -- never anything of the caller's.
+struct CachedBlock {
+  int device;
+  void* ptr;
+  size_t bytes;
+};
+std::mutex g_cache_mutex;
+std::vector<CachedBlock> g_cache;
+constexpr size_t kCacheEntries = 8;
+
+cudaError_t cached_malloc(int device, void** out, size_t bytes, size_t* got_bytes) {
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    size_t best = g_cache.size();
+    for (size_t i = 0; i < g_cache.size(); ++i)
+      if (g_cache[i].device == device && g_cache[i].bytes >= bytes && g_cache[i].bytes <= bytes * 2 + (1u << 20) &&
+          (best == g_cache.size() || g_cache[i].bytes < g_cache[best].bytes))
+        best = i;
+    if (best != g_cache.size()) {
+      *out = g_cache[best].ptr, *got_bytes = g_cache[best].bytes;
+      g_cache.erase(g_cache.begin() + (long)best);
+      return cudaSuccess;
+    }
+  }
+  *got_bytes = bytes;
+  return cudaMalloc(out, bytes);
+}
+
+void cached_free(int device, void* ptr, size_t bytes) {
+  if (!ptr) return;
+  void* evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cache.push_back(CachedBlock { device, ptr, bytes });
+    if (g_cache.size() > kCacheEntries) {
+      evict = g_cache.front().ptr;
+      const int d = g_cache.front().device;
+      g_cache.erase(g_cache.begin());
+      cudaSetDevice(d);
+    }
+  }
+  if (evict) cudaFree(evict);
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <typename T> size_t place(std::vector<unsigned char>& host, const std::vector<T>& v) {
@@ -133,12 +179,13 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   PT_CUDA(cudaSetDevice(device));
   auto* ds = new pt_device_scene;
   ds->device = device;
-  e = cudaMalloc(&ds->arena, total);
+  void* arena = nullptr;
+  e = cached_malloc(device, &arena, total, &ds->arena_bytes);
   if (e != cudaSuccess) {
     delete ds;
     return cuda_fail(e, "cudaMalloc(scene arena)");
   }
-  ds->arena_bytes = total;
+  ds->arena = static_cast<unsigned char*>(arena);
   cudaEvent_t ev0, ev1;
   cudaEventCreate(&ev0), cudaEventCreate(&ev1);
   cudaEventRecord(ev0, 0);
@@ -154,7 +201,7 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   cudaEventElapsedTime(&ms, ev0, ev1);
   cudaEventDestroy(ev0), cudaEventDestroy(ev1);
   if (e != cudaSuccess) {
-    cudaFree(ds->arena);
+    cached_free(device, ds->arena, ds->arena_bytes);
     delete ds;
     return cuda_fail(e, "scene upload");
   }
@@ -244,8 +291,9 @@ int pt_scene_upload(const pt_scene* scene, int device, pt_device_scene** out) {
 void pt_scene_free(pt_device_scene* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaFree(s->arena);
-  if (s->lpt_buf) cudaFree(s->lpt_buf);
+  cudaDeviceSynchronize();  // nothing may still be using the arena when it is handed to the next upload
+  cached_free(s->device, s->arena, s->arena_bytes);
+  cached_free(s->device, s->lpt_buf, s->lpt_ints * sizeof(int));
   delete s;
 }
 
@@ -300,10 +348,12 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
     const int tiles_x = (region->w + kTile - 1) / kTile, tiles_y = (region->h + kTile - 1) / kTile;
     const size_t need = (size_t)pw * ph + 2 * (size_t)tiles_x * tiles_y;
     if (need > scene->lpt_ints) {
-      if (scene->lpt_buf) cudaFree(scene->lpt_buf);
+      cached_free(scene->device, scene->lpt_buf, scene->lpt_ints * sizeof(int));
       scene->lpt_buf = nullptr, scene->lpt_ints = 0;
-      PT_CUDA(cudaMalloc(&scene->lpt_buf, need * sizeof(int)));
-      scene->lpt_ints = need;
+      void* buf = nullptr;
+      size_t got = 0;
+      PT_CUDA(cached_malloc(scene->device, &buf, need * sizeof(int), &got));
+      scene->lpt_buf = static_cast<int*>(buf), scene->lpt_ints = got / sizeof(int);
     }
     int* probe_cost = scene->lpt_buf;
     int* tile_order = probe_cost + (size_t)pw * ph;
@@ -408,7 +458,10 @@ int pt_render_region(int width, int height, int spp, int depth, const pt_camera*
   if (rc != PT_OK) return rc;
   const size_t row_floats = (size_t)region->w * 3;
   float* d_out = nullptr;
-  cudaError_t e = cudaMalloc(&d_out, std::max<size_t>(row_floats * region->h, 1) * sizeof(float));
+  size_t d_out_bytes = 0;
+  void* d_out_v = nullptr;
+  cudaError_t e = cached_malloc(0, &d_out_v, std::max<size_t>(row_floats * region->h, 1) * sizeof(float), &d_out_bytes);
+  d_out = static_cast<float*>(d_out_v);
   if (e != cudaSuccess) {
     pt_scene_free(ds);
     return cuda_fail(e, "cudaMalloc(framebuffer)");
@@ -440,7 +493,8 @@ int pt_render_region(int width, int height, int spp, int depth, const pt_camera*
     g_stats = st;
   }
   for (auto& x : ev) cudaEventDestroy(x);
-  cudaFree(d_out);
+  cudaStreamSynchronize(0);
+  cached_free(0, d_out, d_out_bytes);
   pt_scene_free(ds);
   return rc;
 }
