@@ -173,6 +173,51 @@ def triangle_mesh(aspect=16 / 9, nx=12, nz=6, seed=5):
     return s, _cam(aspect, look_from=(10, 4, 8), vfov=30.0, aperture=0.05, focus=12.0)
 
 
+def cornell(aspect=1.0):
+    """BASELINE config 3: Cornell box.  hittable_t has no rotate/translate and only xy_rect at top level
+    (render.hpp:22-23), so floor / ceiling / side walls / light are thin boxes and the back wall an xy_rect;
+    two boxes are wrapped in constant_medium smoke (white / black), one is plain."""
+    s = Scene()
+    red, white, green = s.lambertian((0.65, 0.05, 0.05)), s.lambertian((0.73, 0.73, 0.73)), s.lambertian((0.12, 0.45, 0.15))
+    light = s.lightsource((15, 15, 15))
+    s.box((555, 0, 0), (556, 555, 555), green)        # left wall
+    s.box((-1, 0, 0), (0, 555, 555), red)             # right wall
+    s.box((213, 554, 227), (343, 555, 332), light)    # ceiling light
+    s.box((0, -1, 0), (555, 0, 555), white)           # floor
+    s.box((0, 555, 0), (555, 556, 555), white)        # ceiling
+    s.rect(0, 555, 0, 555, 555, white)                # back wall (xy_rect, k = z)
+    s.medium_box((130, 0, 65), (295, 165, 230), 0.01, (1, 1, 1))
+    s.medium_box((265, 0, 295), (430, 330, 460), 0.01, (0, 0, 0))
+    s.box((60, 0, 300), (160, 100, 400), white)
+    return s, make_camera((278, 278, -800), (278, 278, 0), (0, 1, 0), 40.0, aspect, 0.0, 10.0, 0.0, 0.0)
+
+
+def motion_blur(aspect=16 / 9, seed=2):
+    """BASELINE config 5: the default scene's 22x22 grid with ALL small Lambertian spheres moving,
+    depth of field (aperture 0.1) and a 0..1 shutter."""
+    rs = np.random.RandomState(seed)
+    f = np.float32
+    s = Scene()
+    s.sphere((0, -1000, 0), 1000, s.lambertian(s.checker((0.2, 0.3, 0.1), (0.9, 0.9, 0.9))))
+    for a in range(-11, 11):
+        for b in range(-11, 11):
+            choose = rs.rand()
+            c = np.array([f(a + 0.9 * rs.rand()), f(0.2), f(b + 0.9 * rs.rand())], dtype=np.float32)
+            if np.linalg.norm(c - np.array([4, 0.2, 0])) <= 0.9:
+                continue
+            if choose < 0.8:
+                c1 = c + np.array([0, f(0.5 * rs.rand()), 0], dtype=np.float32)
+                s.sphere(c, 0.2, s.lambertian(tuple(rs.rand(3) * rs.rand(3))), center1=c1, time0=0.0, time1=1.0)
+            elif choose < 0.95:
+                s.sphere(c, 0.2, s.metal(tuple(0.5 + 0.5 * rs.rand(3)), 0.5 * rs.rand()))
+            else:
+                s.sphere(c, 0.2, s.dielectric(1.5))
+    s.sphere((0, 1, 0), 1.0, s.dielectric(1.5))
+    s.sphere((-4, 1, 0), 1.0, s.lambertian((0.4, 0.2, 0.1)))
+    s.sphere((4, 1, 0), 1.0, s.metal((0.7, 0.6, 0.5), 0.0))
+    return s, make_camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, aspect, 0.1, 10.0, 0.0, 1.0)
+
+
 def random_scene(seed, n_objects=60, aspect=4 / 3):
     """Mixed random scene; the seed decides kinds, materials, order."""
     rs = np.random.RandomState(seed)
@@ -225,5 +270,6 @@ def random_scene(seed, n_objects=60, aspect=4 / 3):
 ALL = {
     "spheres_basic": spheres_basic, "moving": moving, "shapes": shapes, "media": media, "ties": ties,
     "empty": empty, "single_light": single_light, "triangle_mesh": triangle_mesh, "rect_axes": rect_axes,
+    "cornell": cornell,
 }
 REFERENCE_COMPATIBLE = [k for k in ALL if k != "rect_axes"]
