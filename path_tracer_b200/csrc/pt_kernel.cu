@@ -43,7 +43,7 @@ namespace {
 
 constexpr float kTMin = 0.001f;  // render.hpp:40
 #ifndef PT_SCAN_UNROLL
-#define PT_SCAN_UNROLL 4
+#define PT_SCAN_UNROLL 8
 #endif
 constexpr int kScanUnroll = PT_SCAN_UNROLL;  // spheres per hot-loop trip
 #ifndef PT_DEEP_RATE
@@ -395,31 +395,71 @@ PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ da
 
 // The team variant (member m takes elements first, first+stride, ...): out of line and by value, so
 // that it does not sit between the hot loops in the instruction stream.
+template <bool kSmem, bool kMoving, int kStride>
+PT_DEV Best scan_spheres_team(const KeyTable& sc, const float4* __restrict__ data, const SphereAux* aux, int first,
+                              int end, const Ray& r, float a, float f, bool act, int type, Best best) {
+  const float af = filter_a(a);
+  if constexpr (kStride <= 8) {
+    // Teams of 2, 4 or 8: the same unrolled loop as the unit-stride one, with the team's stride as an
+    // immediate.  A chunk is 32 spheres (group sizes are multiples of 32), 32 / kStride of them mine.
+    constexpr int kOwn = kSphereChunk / kStride;
+    constexpr int kUnroll = kOwn < 4 ? kOwn : 4;
+#pragma unroll 1
+    for (int base = first; base < end; base += kSphereChunk) {
+      uint32_t mask = 0;  // my k-th sphere of the chunk (base + k * kStride) ends up at bit kOwn - 1 - k
+#pragma unroll 1
+      for (int it = 0; it < kOwn; it += kUnroll) {
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j)
+          mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, base + (it + j) * kStride, f, r, af), mask, 1);
+      }
+      if (!act) mask = 0;
+      while (mask) {
+        const int k = kOwn - 1 - (31 - __clz((int)mask));
+        mask &= ~(1u << (kOwn - 1 - k));
+        const int i = base + k * kStride;
+        float cx, cy, cz, r2f;
+        sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
+        sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
+      }
+    }
+  } else {
+    const int n_it = (end - first + kStride - 1) / kStride;  // elements of this member
+#pragma unroll 1
+    for (int it0 = 0; it0 < n_it; it0 += kSphereChunk) {
+      uint32_t mask = 0;
+      const int lim = min(kSphereChunk, n_it - it0);
+#pragma unroll 2
+      for (int it = 0; it < lim; ++it)
+        mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, first + (it0 + it) * kStride, f, r, af), mask, 1);
+      if (lim < kSphereChunk) mask <<= (kSphereChunk - lim);  // left-align: element it0 + k at bit 31 - k
+      if (!act) mask = 0;
+      while (mask) {
+        const int it = __clz((int)mask);
+        mask &= ~(0x80000000u >> it);
+        const int i = first + (it0 + it) * kStride;
+        float cx, cy, cz, r2f;
+        sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
+        sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
+      }
+    }
+  }
+  return best;
+}
+
+// The team variants (member m takes elements first, first+stride, ...): out of line and by value, so
+// that they do not sit between the hot loops in the instruction stream.
 template <bool kSmem, bool kMoving>
 __device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __restrict__ data, const SphereAux* aux,
                                                   int first, int end, int stride, Ray r, float a, float f, bool act,
                                                   int type, Best best) {
-  const float af = filter_a(a);
-  const int n_it = (end - first + stride - 1) / stride;  // elements of this member
-#pragma unroll 1
-  for (int it0 = 0; it0 < n_it; it0 += kSphereChunk) {
-    uint32_t mask = 0;
-    const int lim = min(kSphereChunk, n_it - it0);
-#pragma unroll 2
-    for (int it = 0; it < lim; ++it)
-      mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, first + (it0 + it) * stride, f, r, af), mask, 1);
-    if (lim < kSphereChunk) mask <<= (kSphereChunk - lim);  // left-align: element it0 + k at bit 31 - k
-    if (!act) mask = 0;
-    while (mask) {
-      const int it = __clz((int)mask);
-      mask &= ~(0x80000000u >> it);
-      const int i = first + (it0 + it) * stride;
-      float cx, cy, cz, r2f;
-      sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
-      sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
-    }
+  switch (stride) {
+    case 2: return scan_spheres_team<kSmem, kMoving, 2>(sc, data, aux, first, end, r, a, f, act, type, best);
+    case 4: return scan_spheres_team<kSmem, kMoving, 4>(sc, data, aux, first, end, r, a, f, act, type, best);
+    case 8: return scan_spheres_team<kSmem, kMoving, 8>(sc, data, aux, first, end, r, a, f, act, type, best);
+    case 16: return scan_spheres_team<kSmem, kMoving, 16>(sc, data, aux, first, end, r, a, f, act, type, best);
+    default: return scan_spheres_team<kSmem, kMoving, 32>(sc, data, aux, first, end, r, a, f, act, type, best);
   }
-  return best;
 }
 
 template <bool kSmem, bool kMoving>
@@ -1169,7 +1209,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       float best_cost = (float)passes * 1.0f;
       for (int t = 2, lg = 1; t <= 32; t <<= 1, ++lg) {
         const int ps = (n * t + kWaveThreads - 1) / kWaveThreads;
-        const float cost = (float)ps * (1.5f / (float)t + 0.03f * (float)lg);  // measured: strided team scans cost more per test
+        const float cost = (float)ps * (1.15f / (float)t + 0.03f * (float)lg);
         if (cost < best_cost) best_cost = cost, team_size = t, passes = ps;
       }
     }
