@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ namespace {
 thread_local std::string g_error;
 int g_num_gpus = 1;
 int g_team_size_override = 0;
+int g_cull_enabled = 1;
 int g_lpt_enabled = 1;  // pt_debug_set_lpt
 int g_n_express = -1;   // < 0: automatic (pt_debug_set_express)
 int g_kernel_kind = 0;  // 0 = wavefront kernel, 1 = lane kernel (pt_debug_set_kernel)
@@ -69,6 +71,11 @@ struct pt_device_scene {
   unsigned int kernel_launches = 0;  // kernels launched since creation (probe, tile sort, render)
   unsigned long long paths_launched = 0;
   LaunchInfo last_launch {};
+  // chunk boxes (pt_pack.h): what they are computed from, and the shutter interval they were last computed for
+  PackedScene geo;
+  bool cull_valid = false;
+  int cull_mode = -1;
+  float cull_time0 = 0.f, cull_time1 = 0.f;
 };
 
 namespace {
@@ -229,12 +236,41 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   d.n_texture_texels = tex_bytes / 3;
   d.n_materials = (uint32_t)ps.materials.size();
   d.n_textures = (uint32_t)ps.textures.size();
+  d.off_sphere_box = ps.off_sphere_box, d.off_moving_box = ps.off_moving_box;
+  d.n_sphere_chunks = (uint32_t)ps.sphere_chunk_open.size(), d.n_moving_chunks = (uint32_t)ps.moving_chunk_open.size();
+  d.cull_bound[0] = d.cull_bound[1] = d.cull_bound[2] = 0.f;  // no culling until update_chunk_boxes()
+  ds->geo.sphere_geo.swap(ps.sphere_geo), ds->geo.moving_geo.swap(ps.moving_geo);
+  ds->geo.sphere_chunk_open.swap(ps.sphere_chunk_open), ds->geo.moving_chunk_open.swap(ps.moving_chunk_open);
   ds->queue_heads = reinterpret_cast<unsigned long long*>(ds->arena + o_heads);
   ds->counters = ds->queue_heads + kCounterSlots;
   ds->heavy_ctrl = reinterpret_cast<unsigned int*>(ds->arena + o_hctrl);
   ds->heavy_ready = reinterpret_cast<unsigned int*>(ds->arena + o_hready);
   ds->heavy_entries = reinterpret_cast<float*>(ds->arena + o_hentries);
   *out = ds;
+  return PT_OK;
+}
+
+// The chunk boxes of moving spheres cover their sweep over the camera's shutter interval, so they are
+// (re)computed when a render brings a different interval: a few hundred boxes, one small copy ordered
+// before the launch on the same stream.  Renders of ONE device scene must therefore not overlap on
+// different streams with different shutter intervals.
+int update_chunk_boxes(pt_device_scene* scene, const pt_camera* cam, cudaStream_t st) {
+  if (scene->cull_valid && scene->cull_mode == g_cull_enabled && std::memcmp(&scene->cull_time0, &cam->time0, 4) == 0 &&
+      std::memcmp(&scene->cull_time1, &cam->time1, 4) == 0)
+    return PT_OK;
+  CullBoxes boxes;
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  compute_cull_boxes(scene->geo, g_cull_enabled ? cam->time0 : nan, g_cull_enabled ? cam->time1 : nan, boxes);
+  unsigned char* blob = const_cast<unsigned char*>(scene->desc.blob);
+  if (!boxes.sphere.empty())
+    PT_CUDA(cudaMemcpyAsync(blob + scene->desc.off_sphere_box, boxes.sphere.data(), boxes.sphere.size() * sizeof(float),
+                            cudaMemcpyHostToDevice, st));
+  if (!boxes.moving.empty())
+    PT_CUDA(cudaMemcpyAsync(blob + scene->desc.off_moving_box, boxes.moving.data(), boxes.moving.size() * sizeof(float),
+                            cudaMemcpyHostToDevice, st));
+  for (int k = 0; k < 3; ++k) scene->desc.cull_bound[k] = boxes.bound[k];
+  scene->cull_valid = true, scene->cull_mode = g_cull_enabled;
+  scene->cull_time0 = cam->time0, scene->cull_time1 = cam->time1;
   return PT_OK;
 }
 
@@ -311,6 +347,10 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
     // render.hpp:58,91: no bounce allowed -> every sample returns black
     PT_CUDA(cudaMemset2DAsync(d_out, out_row_pitch * sizeof(float), 0, (size_t)region->w * 3 * sizeof(float), region->h, st));
     return PT_OK;
+  }
+  {
+    const int crc = update_chunk_boxes(scene, camera, st);
+    if (crc != PT_OK) return crc;
   }
   RenderParams p;
   p.scene = scene->desc;
@@ -401,6 +441,10 @@ int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* sc
 }
 
 // Debug aid (not part of pt_abi.h): force the launch team size (0 = automatic).
+int pt_debug_set_cull(int on) {
+  g_cull_enabled = on ? 1 : 0;
+  return PT_OK;
+}
 int pt_debug_set_team_size(int t) {
   g_team_size_override = t;
   return PT_OK;

@@ -104,6 +104,8 @@ struct SceneView {
   const float4* rect;
   const float4* triangle;
   const float4* box;
+  const float4* sphere_box;  // chunk boxes, set 0 first
+  const float4* moving_box;
 };
 
 template <bool kSmem> PT_DEV float4 ld4(const float4* p) {
@@ -320,19 +322,17 @@ PT_DEV void team_merge(const SceneDesc& sc, Best& best, int team_size) {
   }
 }
 
-// Two-phase sphere scan over elements first, first+stride, ... < end (kMoving: 2 float4 per sphere).
-// Phase 1 is branch-free and only collects a bitmask of spheres whose discriminant is positive;
-// phase 2 computes exact roots for the set bits.  The stride-1 instance is the steady-state hot
-// loop (4 spheres per trip so that it stays inside the instruction cache).
-// Centre of sphere i at the ray's time (sphere.hpp:51-56), exactly as the reference computes it.
+// Two-phase sphere test.  Phase 1 is branch-free and only collects a bitmask of spheres whose
+// discriminant is positive; phase 2 computes exact roots for the set bits.
+// Centre of the sphere at slot `p` ({c, r*r} entry; a moving sphere's {c1 - c0} is 32 entries further,
+// pt_packed.h) at the ray's time (sphere.hpp:51-56), exactly as the reference computes it.
 template <bool kSmem, bool kMoving>
-PT_DEV void sphere_center(const float4* __restrict__ data, int i, float f, float& cx, float& cy, float& cz, float& r2_filter) {
+PT_DEV void sphere_center(const float4* __restrict__ p, float f, float& cx, float& cy, float& cz, float& r2_filter) {
+  const float4 s = ld4<kSmem>(p);
   if constexpr (kMoving) {
-    const float4 s = ld4<kSmem>(data + 2 * i);
-    const float4 v = ld4<kSmem>(data + 2 * i + 1);
+    const float4 v = ld4<kSmem>(p + 2 * kSphereChunk);
     cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2_filter = s.w;  // sphere.hpp:55
   } else {
-    const float4 s = ld4<kSmem>(data + i);
     cx = s.x, cy = s.y, cz = s.z, r2_filter = s.w;
   }
 }
@@ -340,7 +340,7 @@ PT_DEV void sphere_center(const float4* __restrict__ data, int i, float f, float
 // CONSERVATIVE MISS FILTER (the hot instruction sequence of the whole renderer).  The reference
 // evaluates  disc = b*b - a*c,  b = dot(oc, d),  c = dot(oc, oc) - r*r  with 17 separately rounded
 // operations and hits only if disc > 0 (sphere.hpp:68-74).  Parity needs that exact sequence ONLY
-// for spheres that can be hit; for the other ~99 % it is enough to PROVE disc <= 0.  The filter
+// for spheres that can be hit; for the others it is enough to PROVE disc <= 0.  The filter
 // evaluates, with fused multiply-adds (11 operations),
 //     test = b'^2 - a(1-k) * (|oc|^2 - r^2 (1+e)),   e = 2k / (1-k)
 // which in exact arithmetic equals  disc + k * a * (|oc|^2 + r^2).  Either evaluation is within
@@ -354,9 +354,9 @@ PT_DEV float filter_a(float a) { return fmul(a, 1.0f - kFilterK); }
 // Returns the bits of -test: the SIGN BIT is set for every sphere the filter lets through (and, harmlessly,
 // for -0 and some NaNs), so the per-lane candidate mask is collected with one funnel shift per sphere.
 template <bool kSmem, bool kMoving>
-PT_DEV uint32_t sphere_filter_bits(const float4* __restrict__ data, int i, float f, const Ray& r, float a_filter) {
+PT_DEV uint32_t sphere_filter_bits(const float4* __restrict__ p, float f, const Ray& r, float a_filter) {
   float cx, cy, cz, r2f;
-  sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
+  sphere_center<kSmem, kMoving>(p, f, cx, cy, cz, r2f);
   const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
   const float b = __fmaf_rn(ocx, r.d.x, __fmaf_rn(ocy, r.d.y, fmul(ocz, r.d.z)));
   const float c = __fmaf_rn(ocx, ocx, __fmaf_rn(ocy, ocy, __fmaf_rn(ocz, ocz, -r2f)));
@@ -367,108 +367,140 @@ PT_DEV float exact_r2(const SphereAux* aux, int i) {
   return fmul(radius, radius);  // sphere.hpp:71
 }
 
-// The steady-state hot loop (stride 1): 4 spheres per trip so that it stays inside the instruction cache;
-// group sizes are padded to kSphereChunk with spheres that can never be hit (pt_pack.cpp).
-template <bool kSmem, bool kMoving>
-PT_DEV void scan_spheres_unit(const SceneDesc& sc, const float4* __restrict__ data, const SphereAux* aux, int first,
-                              int end, const Ray& r, float a, float f, bool act, int type, Best& best) {
-  const float af = filter_a(a);
-#pragma unroll 1
-  for (int base = first; base < end; base += kSphereChunk) {
-    uint32_t mask = 0;  // sphere base + k ends up at bit 31 - k
-#pragma unroll 1
-    for (int it = 0; it < kSphereChunk; it += kScanUnroll) {
-#pragma unroll
-      for (int j = 0; j < kScanUnroll; ++j)
-        mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, base + it + j, f, r, af), mask, 1);
-    }
-    if (!act) mask = 0;
-    while (mask) {
-      const int j = __clz((int)mask);
-      mask &= ~(0x80000000u >> j);
-      float cx, cy, cz, r2f;
-      sphere_center<kSmem, kMoving>(data, base + j, f, cx, cy, cz, r2f);
-      sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, base + j), make_id(type, base + j));
-    }
-  }
+// CHUNK CULLING.  Spheres come in chunks of 16 spatially close ones, each with a bounding box
+// (pt_packed.h); a ray scans only the chunks whose box it crosses between t = 0 and the running
+// closest hit.  The result is the reference's for ANY set of skipped chunks that cannot contain an
+// accepted root (the winner rule is order independent), so what has to hold is: "the reference accepts
+// a root of sphere i" => "the box test of i's chunk passes".  The boxes are grown on the host by a
+// margin that covers the rounding of the reference's own root, of the centre and of this slab test
+// for every origin with max |coordinate| <= cull_bound[set] (pt_pack.cpp, DESIGN.md "chunk
+// culling"); the last set is infinite boxes and serves every other ray.  The slab test runs on
+// 1/d clamped to +-2^60: for a component below 2^-60 the plane distances then come out within
+// t / 2^60 of zero instead of exactly there, far inside the margin, as long as the direction's largest
+// component lies in [2^-20, 2^20] -- rays outside that range are not culled at all.
+struct CullRay {
+  float ix, iy, iz;  // clamped 1 / d
+  float qx, qy, qz;  // -o * (1 / d)
+};
+constexpr float kCullInvMax = 1.152921504606847e18f;  // 2^60
+constexpr float kCullDirMin = 9.5367431640625e-7f;    // 2^-20
+constexpr float kCullDirMax = 1048576.f;              // 2^20
+PT_DEV float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Returns the box set of this ray.
+PT_DEV int make_cull_ray(const SceneDesc& sc, const Ray& r, CullRay& c) {
+  const float dmax = fmaxf(fmaxf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z));
+  const float omax = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z));
+  int set = (kCullSets - 1) - ((omax <= sc.cull_bound[0]) + (omax <= sc.cull_bound[1]) + (omax <= sc.cull_bound[2]));
+  if (!(dmax >= kCullDirMin && dmax <= kCullDirMax)) set = kCullSets - 1;
+  c.ix = fminf(fmaxf(rcp_fast(r.d.x), -kCullInvMax), kCullInvMax);
+  c.iy = fminf(fmaxf(rcp_fast(r.d.y), -kCullInvMax), kCullInvMax);
+  c.iz = fminf(fmaxf(rcp_fast(r.d.z), -kCullInvMax), kCullInvMax);
+  c.qx = -(r.o.x * c.ix), c.qy = -(r.o.y * c.iy), c.qz = -(r.o.z * c.iz);
+  return set;
+}
+// Bits of (entry - exit) of the ray's interval inside the box, clipped to [0, tmax]: SIGN BIT set <=>
+// the ray crosses the box there (fminf / fmaxf drop NaNs, which only ever widens the interval).
+template <bool kSmem> PT_DEV uint32_t chunk_bits(const float4* __restrict__ box, const CullRay& c, float tmax) {
+  const float4 lo = ld4<kSmem>(box), hi = ld4<kSmem>(box + 1);
+  const float ax = __fmaf_rn(lo.x, c.ix, c.qx), bx = __fmaf_rn(hi.x, c.ix, c.qx);
+  const float ay = __fmaf_rn(lo.y, c.iy, c.qy), by = __fmaf_rn(hi.y, c.iy, c.qy);
+  const float az = __fmaf_rn(lo.z, c.iz, c.qz), bz = __fmaf_rn(hi.z, c.iz, c.qz);
+  const float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+  const float t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+  return __float_as_uint(t_in - t_out);
 }
 
-// The team variant (member m takes elements first, first+stride, ...): out of line and by value, so
-// that it does not sit between the hot loops in the instruction stream.
-template <bool kSmem, bool kMoving, int kStride>
-PT_DEV Best scan_spheres_team(const KeyTable& sc, const float4* __restrict__ data, const SphereAux* aux, int first,
-                              int end, const Ray& r, float a, float f, bool act, int type, Best best) {
+// Scan the chunks [first_el / 16, end_el / 16) of one sphere group for one ray.  Every lane first
+// collects the bitmask of chunks its ray crosses (same box for all lanes: broadcast loads), then
+// pops its OWN next chunk and filters its share of the 16 spheres, kTeam lanes per ray: own k-th
+// sphere = slot rot + k * kTeam of the doubled chunk, rot = lane & 15, so that the lanes of a warp,
+// each on a different chunk, read different shared-memory banks.
+template <bool kSmem, bool kMoving, int kTeam, typename Keys>
+PT_DEV void scan_sphere_chunks(const Keys& sc, const float4* __restrict__ data, const float4* __restrict__ boxes,
+                               const SphereAux* aux, int first_el, int end_el, int rot, const Ray& r, float a,
+                               float f, const CullRay& cr, bool act, int type, Best& best) {
+  constexpr int kOwn = kSphereChunk / kTeam;
+  constexpr int kUnroll = kOwn < kScanUnroll ? kOwn : kScanUnroll;
+  constexpr int kSlots = kMoving ? 4 * kSphereChunk : 2 * kSphereChunk;  // float4 per chunk
   const float af = filter_a(a);
-  if constexpr (kStride <= 8) {
-    // Teams of 2, 4 or 8: the same unrolled loop as the unit-stride one, with the team's stride as an
-    // immediate.  A chunk is 32 spheres (group sizes are multiples of 32), 32 / kStride of them mine.
-    constexpr int kOwn = kSphereChunk / kStride;
-    constexpr int kUnroll = kOwn < 4 ? kOwn : 4;
+  const int c_end = end_el / kSphereChunk;
 #pragma unroll 1
-    for (int base = first; base < end; base += kSphereChunk) {
-      uint32_t mask = 0;  // my k-th sphere of the chunk (base + k * kStride) ends up at bit kOwn - 1 - k
+  for (int cb = first_el / kSphereChunk; cb < c_end; cb += 32) {
+    const int nb = min(32, c_end - cb);
+    float tmax = act ? best.t : -1.f;
+    uint32_t hits = 0;  // chunk cb + k at bit nb - 1 - k
+    if constexpr (kTeam == 1) {
+#pragma unroll 2
+      for (int k = 0; k < nb; ++k) hits = __funnelshift_l(chunk_bits<kSmem>(boxes + 2 * (cb + k), cr, tmax), hits, 1);
+    } else {
+      // The team shares the box tests: member m takes chunks m, m + kTeam, ... against the smallest of the
+      // members' running closest hits, and the members' bits are OR-ed together (the whole warp is
+      // converged here: the loop bounds depend on the group only).
+#pragma unroll
+      for (int o = kTeam >> 1; o > 0; o >>= 1) tmax = fminf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+#pragma unroll 1
+      for (int k = rot & (kTeam - 1); k < nb; k += kTeam)
+        hits |= (chunk_bits<kSmem>(boxes + 2 * (cb + k), cr, tmax) >> 31) << (nb - 1 - k);
+#pragma unroll
+      for (int o = kTeam >> 1; o > 0; o >>= 1) hits |= __shfl_xor_sync(0xffffffffu, hits, o);
+    }
+#pragma unroll 1
+    while (hits) {
+      const int top = 31 - __clz((int)hits);
+      hits &= ~(1u << top);
+      const int chunk = cb + (nb - 1 - top);
+      const float4* base = data + chunk * kSlots + rot;
+      uint32_t mask = 0;  // own k-th sphere at bit kOwn - 1 - k
 #pragma unroll 1
       for (int it = 0; it < kOwn; it += kUnroll) {
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j)
-          mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, base + (it + j) * kStride, f, r, af), mask, 1);
+          mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(base + (it + j) * kTeam, f, r, af), mask, 1);
       }
-      if (!act) mask = 0;
       while (mask) {
-        const int k = kOwn - 1 - (31 - __clz((int)mask));
-        mask &= ~(1u << (kOwn - 1 - k));
-        const int i = base + k * kStride;
+        const int mt = 31 - __clz((int)mask);
+        mask &= ~(1u << mt);
+        const int k = kOwn - 1 - mt;
+        const int i = chunk * kSphereChunk + ((rot + k * kTeam) & (kSphereChunk - 1));
         float cx, cy, cz, r2f;
-        sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
+        sphere_center<kSmem, kMoving>(base + k * kTeam, f, cx, cy, cz, r2f);
         sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
       }
     }
-  } else {
-    const int n_it = (end - first + kStride - 1) / kStride;  // elements of this member
-#pragma unroll 1
-    for (int it0 = 0; it0 < n_it; it0 += kSphereChunk) {
-      uint32_t mask = 0;
-      const int lim = min(kSphereChunk, n_it - it0);
-#pragma unroll 2
-      for (int it = 0; it < lim; ++it)
-        mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(data, first + (it0 + it) * kStride, f, r, af), mask, 1);
-      if (lim < kSphereChunk) mask <<= (kSphereChunk - lim);  // left-align: element it0 + k at bit 31 - k
-      if (!act) mask = 0;
-      while (mask) {
-        const int it = __clz((int)mask);
-        mask &= ~(0x80000000u >> it);
-        const int i = first + (it0 + it) * kStride;
-        float cx, cy, cz, r2f;
-        sphere_center<kSmem, kMoving>(data, i, f, cx, cy, cz, r2f);
-        sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
-      }
-    }
+  }
+}
+
+// The team variants (kTeam lanes share a ray, each with its own partial winner): out of line and by
+// value, so that they do not sit between the hot loops in the instruction stream.
+template <bool kSmem, bool kMoving>
+__device__ __noinline__ Best scan_spheres_team(KeyTable sc, const float4* __restrict__ data,
+                                               const float4* __restrict__ boxes, const SphereAux* aux, int first_el,
+                                               int end_el, int team_size, Ray r, float a, float f, CullRay cr, bool act,
+                                               int type, Best best) {
+  const int rot = (int)(threadIdx.x & (kSphereChunk - 1));
+  switch (team_size) {
+    case 2: scan_sphere_chunks<kSmem, kMoving, 2>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+    case 4: scan_sphere_chunks<kSmem, kMoving, 4>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+    case 8: scan_sphere_chunks<kSmem, kMoving, 8>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+    default: scan_sphere_chunks<kSmem, kMoving, 16>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
   }
   return best;
 }
 
-// The team variants (member m takes elements first, first+stride, ...): out of line and by value, so
-// that they do not sit between the hot loops in the instruction stream.
 template <bool kSmem, bool kMoving>
-__device__ __noinline__ Best scan_spheres_strided(KeyTable sc, const float4* __restrict__ data, const SphereAux* aux,
-                                                  int first, int end, int stride, Ray r, float a, float f, bool act,
-                                                  int type, Best best) {
-  switch (stride) {
-    case 2: return scan_spheres_team<kSmem, kMoving, 2>(sc, data, aux, first, end, r, a, f, act, type, best);
-    case 4: return scan_spheres_team<kSmem, kMoving, 4>(sc, data, aux, first, end, r, a, f, act, type, best);
-    case 8: return scan_spheres_team<kSmem, kMoving, 8>(sc, data, aux, first, end, r, a, f, act, type, best);
-    case 16: return scan_spheres_team<kSmem, kMoving, 16>(sc, data, aux, first, end, r, a, f, act, type, best);
-    default: return scan_spheres_team<kSmem, kMoving, 32>(sc, data, aux, first, end, r, a, f, act, type, best);
-  }
-}
-
-template <bool kSmem, bool kMoving>
-PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, const SphereAux* aux, int first, int end,
-                         int stride, const Ray& r, float a, float f, bool act, int type, Best& best) {
-  if (stride == 1)
-    scan_spheres_unit<kSmem, kMoving>(sc, data, aux, first, end, r, a, f, act, type, best);
+PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, const float4* __restrict__ boxes,
+                         const SphereAux* aux, int first_el, int end_el, int team_size, const Ray& r, float a, float f,
+                         const CullRay& cr, bool act, int type, Best& best) {
+  if (team_size == 1)
+    scan_sphere_chunks<kSmem, kMoving, 1>(sc, data, boxes, aux, first_el, end_el, (int)(threadIdx.x & (kSphereChunk - 1)),
+                                          r, a, f, cr, act, type, best);
   else
-    best = scan_spheres_strided<kSmem, kMoving>(key_table(sc), data, aux, first, end, stride, r, a, f, act, type, best);
+    best = scan_spheres_team<kSmem, kMoving>(key_table(sc), data, boxes, aux, first_el, end_el, team_size, r, a, f, cr,
+                                             act, type, best);
 }
 
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
@@ -479,17 +511,22 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
                         int team_size) {
   Best best { kInf, -1 };
   const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant
+  CullRay cr;
+  const int cull_set = make_cull_ray(sc, r, cr);
+  const float4* sphere_boxes = sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
+  const float4* moving_boxes = sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks;
   const int n_groups = (int)sc.n_groups;
   for (int gi = 0; gi < n_groups; ++gi) {
     const Group g = sv.groups[gi];
     const int first = g.begin + member, end = g.begin + g.count;
     switch (g.type) {
       case G_SPHERE:
-        scan_spheres<kSmem, false>(sc, sv.sphere, sc.sphere_aux, first, end, team_size, r, a, 0.f, act, G_SPHERE, best);
+        scan_spheres<kSmem, false>(sc, sv.sphere, sphere_boxes, sc.sphere_aux, g.begin, end, team_size, r, a, 0.f, cr, act,
+                                   G_SPHERE, best);
         break;
       case G_MOVING_SPHERE:
-        scan_spheres<kSmem, true>(sc, sv.moving, sc.moving_aux, first, end, team_size, r, a,
-                                  fdiv(fsub(r.tm, g.time0), g.den), act, G_MOVING_SPHERE, best);
+        scan_spheres<kSmem, true>(sc, sv.moving, moving_boxes, sc.moving_aux, g.begin, end, team_size, r, a,
+                                  fdiv(fsub(r.tm, g.time0), g.den), cr, act, G_MOVING_SPHERE, best);
         break;
       case G_RECT: {
         if (act)
@@ -605,12 +642,12 @@ PT_DEV int build_record(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       V3 center;
       const SphereAux* aux;
       if (type == G_SPHERE) {
-        const float4 s = smem ? sv.sphere[idx] : __ldg(sv.sphere + idx);
+        const float4 s = smem ? sv.sphere[sphere_slot(idx)] : __ldg(sv.sphere + sphere_slot(idx));
         center = v3(s.x, s.y, s.z);
         aux = sc.sphere_aux + idx;
       } else {
-        const float4 s = smem ? sv.moving[2 * idx] : __ldg(sv.moving + 2 * idx);
-        const float4 v = smem ? sv.moving[2 * idx + 1] : __ldg(sv.moving + 2 * idx + 1);
+        const float4 s = smem ? sv.moving[moving_slot(idx)] : __ldg(sv.moving + moving_slot(idx));
+        const float4 v = smem ? sv.moving[moving_slot(idx) + 2 * kSphereChunk] : __ldg(sv.moving + moving_slot(idx) + 2 * kSphereChunk);
         aux = sc.moving_aux + idx;
         center = moving_center(v3(s.x, s.y, s.z), v3(v.x, v.y, v.z), fdiv(fsub(r.tm, aux->time0), aux->den));
       }
@@ -812,13 +849,13 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
   for (;;) {
     // ---- (R) re-pack: the queue is dry for this warp and at most half of its teams still own a
     // pixel -> move the survivors into teams twice (or more) as large.
-    if (team_size < 32) {
+    if (team_size < kSphereChunk) {
       const unsigned can_fetch = __ballot_sync(0xffffffffu, !live && !exhausted_queue);
       const unsigned leaders = __ballot_sync(0xffffffffu, live && member == 0);
       const int k_live = __popc(leaders);
       if (can_fetch == 0u && k_live > 0 && 2 * k_live * team_size <= 32) {
         int new_size = team_size;
-        while (2 * k_live * new_size <= 32) new_size <<= 1;
+        while (2 * k_live * new_size <= 32 && new_size < kSphereChunk) new_size <<= 1;
         const int new_team = lane / new_size;
         const bool keep = new_team < k_live;
         const int src = keep ? (int)__fns(leaders, 0u, new_team + 1) : lane;  // leader lane of the new_team-th live team
@@ -990,6 +1027,8 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
   sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
   sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
+  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
+  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   unsigned int n_scans = 0;
@@ -1121,6 +1160,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
   sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
   sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
+  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
+  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1207,7 +1248,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     int team_size = 1, passes = (n + kWaveThreads - 1) / kWaveThreads;
     {
       float best_cost = (float)passes * 1.0f;
-      for (int t = 2, lg = 1; t <= 32; t <<= 1, ++lg) {
+      for (int t = 2, lg = 1; t <= kSphereChunk; t <<= 1, ++lg) {
         const int ps = (n * t + kWaveThreads - 1) / kWaveThreads;
         const float cost = (float)ps * (1.15f / (float)t + 0.03f * (float)lg);
         if (cost < best_cost) best_cost = cost, team_size = t, passes = ps;
@@ -1485,7 +1526,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
   if (q.team_size <= 0) {
     const unsigned long long lanes = (unsigned long long)grid * kBlockThreads;
     int t = 1;
-    while (t < 32 && pixels * (unsigned long long)t * 2ull < lanes * (unsigned long long)kMinPixelsPerTeam) t <<= 1;
+    while (t < kSphereChunk && pixels * (unsigned long long)t * 2ull < lanes * (unsigned long long)kMinPixelsPerTeam) t <<= 1;
     q.team_size = t;
   }
   if (info) info->grid = grid, info->block = kBlockThreads, info->smem_bytes = (int)dyn, info->blocks_per_sm = per_sm, info->staged = smem, info->team_size = q.team_size;

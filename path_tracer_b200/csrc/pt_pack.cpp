@@ -12,6 +12,7 @@
 //   -1 / density             constant_medium.hpp:20
 #include "pt_pack.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -25,15 +26,21 @@ struct f4 {
   float x, y, z, w;
 };
 
+struct RawSphere {
+  f4 head;  // {c0, r*r inflated for the miss filter}
+  f4 dv;    // {c1 - c0, 0}: moving spheres only
+  SphereAux aux;
+  SphereGeo geo;
+  bool outsized;  // never culled, kept apart from the k-d ordered chunks
+};
+
 struct MovingClass {
   float time0, time1;
-  std::vector<f4> data;  // 2 per sphere
-  std::vector<SphereAux> aux;
+  std::vector<RawSphere> items;
 };
 
 struct Segment {
-  std::vector<f4> sph;
-  std::vector<SphereAux> sph_aux;
+  std::vector<RawSphere> sph;
   std::vector<MovingClass> classes;
   std::vector<f4> rect;
   std::vector<ObjAux> rect_aux;
@@ -44,42 +51,86 @@ struct Segment {
   bool empty() const { return sph.empty() && classes.empty() && rect.empty() && tri.empty() && box.empty(); }
 };
 
+float mid_coord(const RawSphere& s, int axis) { return 0.5f * s.geo.c0[axis] + 0.5f * s.geo.c1[axis]; }
+
+// k-d order: split at the multiple of kSphereChunk nearest to the median along the widest axis of the
+// centres, so that every run of kSphereChunk spheres is a compact cluster (all chunks but one are full).
+void kd_order(std::vector<RawSphere>& v, size_t lo, size_t hi) {
+  const size_t n = hi - lo;
+  if (n <= (size_t)kSphereChunk) return;
+  int axis = 0;
+  float widest = -1.f;
+  for (int k = 0; k < 3; ++k) {
+    float mn = std::numeric_limits<float>::infinity(), mx = -mn;
+    for (size_t i = lo; i < hi; ++i) mn = std::min(mn, mid_coord(v[i], k)), mx = std::max(mx, mid_coord(v[i], k));
+    if (mx - mn > widest) widest = mx - mn, axis = k;
+  }
+  const size_t mid = lo + ((n / 2 + kSphereChunk - 1) / kSphereChunk) * kSphereChunk;
+  std::nth_element(v.begin() + (long)lo, v.begin() + (long)mid, v.begin() + (long)hi,
+                   [axis](const RawSphere& a, const RawSphere& b) { return mid_coord(a, axis) < mid_coord(b, axis); });
+  kd_order(v, lo, mid);
+  kd_order(v, mid, hi);
+}
+
 struct Builder {
   std::vector<Group> groups;
   std::vector<f4> sph, mov, rect, tri, box;
   PackedScene& out;
   explicit Builder(PackedScene& o) : out(o) {}
 
-  static void pad_spheres(std::vector<f4>& data, std::vector<SphereAux>& aux, int per_sphere) {
+  static RawSphere padding() {
     // A padding sphere can never become a candidate: r*r = -inf makes
     // c = dot(oc,oc) - r*r = +inf, so discriminant = b*b - a*c is -inf or NaN.
-    const float ninf = -std::numeric_limits<float>::infinity();
-    while (aux.size() % kSphereChunk) {
-      data.push_back(f4 { 0.f, 0.f, 0.f, ninf });
-      if (per_sphere == 2) data.push_back(f4 { 0.f, 0.f, 0.f, 0.f });
-      SphereAux a {};
-      a.radius = 1.f, a.material = -1, a.key = std::numeric_limits<int32_t>::min();
-      aux.push_back(a);
+    RawSphere p {};
+    p.head = f4 { 0.f, 0.f, 0.f, -std::numeric_limits<float>::infinity() };
+    p.dv = f4 { 0.f, 0.f, 0.f, 0.f };
+    p.aux.radius = 1.f, p.aux.material = -1, p.aux.key = std::numeric_limits<int32_t>::min();
+    p.geo.valid = false;
+    return p;
+  }
+
+  // Chunk layout of pt_packed.h: outsized spheres first (chunks that are never culled), then the k-d
+  // ordered rest; every chunk's entries are written twice in a row.
+  static int emit_spheres(std::vector<RawSphere> items, bool moving, std::vector<f4>& data,
+                          std::vector<SphereAux>& aux, std::vector<SphereGeo>& geo, std::vector<unsigned char>& open) {
+    std::vector<RawSphere> ordered;
+    size_t n_open_chunks = 0;
+    for (const RawSphere& s : items)
+      if (s.outsized) ordered.push_back(s);
+    while (ordered.size() % kSphereChunk) ordered.push_back(padding());
+    n_open_chunks = ordered.size() / kSphereChunk;
+    std::vector<RawSphere> rest;
+    for (const RawSphere& s : items)
+      if (!s.outsized) rest.push_back(s);
+    kd_order(rest, 0, rest.size());
+    ordered.insert(ordered.end(), rest.begin(), rest.end());
+    while (ordered.size() % kSphereChunk) ordered.push_back(padding());
+    for (size_t c = 0; c < ordered.size() / kSphereChunk; ++c) {
+      const RawSphere* ch = ordered.data() + c * kSphereChunk;
+      for (int rep = 0; rep < 2; ++rep)
+        for (int k = 0; k < kSphereChunk; ++k) data.push_back(ch[k].head);
+      if (moving)
+        for (int rep = 0; rep < 2; ++rep)
+          for (int k = 0; k < kSphereChunk; ++k) data.push_back(ch[k].dv);
+      for (int k = 0; k < kSphereChunk; ++k) aux.push_back(ch[k].aux), geo.push_back(ch[k].geo);
+      open.push_back(c < n_open_chunks ? 1 : 0);
     }
+    return (int)ordered.size();
   }
 
   void flush(Segment& s) {
     if (!s.sph.empty()) {
-      pad_spheres(s.sph, s.sph_aux, 1);
       Group g {};
-      g.type = G_SPHERE, g.begin = (int32_t)out.sphere_aux.size(), g.count = (int32_t)s.sph_aux.size();
+      g.type = G_SPHERE, g.begin = (int32_t)out.sphere_aux.size();
+      g.count = emit_spheres(s.sph, false, sph, out.sphere_aux, out.sphere_geo, out.sphere_chunk_open);
       groups.push_back(g);
-      sph.insert(sph.end(), s.sph.begin(), s.sph.end());
-      out.sphere_aux.insert(out.sphere_aux.end(), s.sph_aux.begin(), s.sph_aux.end());
     }
     for (auto& c : s.classes) {
-      pad_spheres(c.data, c.aux, 2);
       Group g {};
-      g.type = G_MOVING_SPHERE, g.begin = (int32_t)out.moving_aux.size(), g.count = (int32_t)c.aux.size();
+      g.type = G_MOVING_SPHERE, g.begin = (int32_t)out.moving_aux.size();
+      g.count = emit_spheres(c.items, true, mov, out.moving_aux, out.moving_geo, out.moving_chunk_open);
       g.time0 = c.time0, g.den = c.time1 - c.time0;
       groups.push_back(g);
-      mov.insert(mov.end(), c.data.begin(), c.data.end());
-      out.moving_aux.insert(out.moving_aux.end(), c.aux.begin(), c.aux.end());
     }
     if (!s.rect_aux.empty()) {
       Group g {};
@@ -106,6 +157,16 @@ struct Builder {
   }
 };
 
+// |centre| + |radius|, the largest over the sphere's own motion
+double sphere_extent(const pt_sphere& s) {
+  double e = 0;
+  for (int end = 0; end < 2; ++end) {
+    const float* c = end ? s.center1 : s.center0;
+    e = std::max(e, std::sqrt((double)c[0] * c[0] + (double)c[1] * c[1] + (double)c[2] * c[2]));
+  }
+  return e + std::fabs((double)s.radius);
+}
+
 uint32_t append(std::vector<unsigned char>& blob, const void* p, size_t bytes) {
   while (blob.size() % 16) blob.push_back(0);
   const uint32_t off = (uint32_t)blob.size();
@@ -115,6 +176,98 @@ uint32_t append(std::vector<unsigned char>& blob, const void* p, size_t bytes) {
 }
 
 }  // namespace
+
+// CHUNK BOXES.  A sphere the reference hits at parameter t puts the point o + t d within
+// sqrt(r^2 + E) of the (float) centre, E = 48 u (|o - c| + r)^2: the residual of the float root in the
+// exact quadratic (error analysis in DESIGN.md, "chunk culling").  A box set serves every origin with
+// max |coordinate| <= bound, so |o - c| + r <= sqrt(3) bound + S with S = max (|c| + |r|) over the culled
+// spheres, and each chunk's box is the union of its spheres' boxes (over the sweep of the moving
+// ones) grown by  m = 2 min(sqrt(E), E / (2 r_min)) + 1e-6 (bound + S) (2 + |f|max);  the second term
+// covers the rounding of the centre, of the slab test itself and of the ray time.
+void compute_cull_boxes(const PackedScene& ps, float cam_time0, float cam_time1, CullBoxes& out) {
+  const double inf = std::numeric_limits<double>::infinity();
+  struct Range {
+    double lo[3], hi[3];
+    bool any;
+  };
+  const std::vector<SphereGeo>* geos[2] = { &ps.sphere_geo, &ps.moving_geo };
+  const std::vector<unsigned char>* opens[2] = { &ps.sphere_chunk_open, &ps.moving_chunk_open };
+  std::vector<Range> ranges[2];
+  double s_max = 0, r_min = inf, f_abs_max = 0;
+  bool usable = cam_time0 == cam_time0 && cam_time1 == cam_time1 && std::isfinite(cam_time0) && std::isfinite(cam_time1);
+  const double ct_lo = std::min(cam_time0, cam_time1), ct_hi = std::max(cam_time0, cam_time1);
+  const double ct_pad = 1e-6 * (std::fabs(ct_lo) + std::fabs(ct_hi));
+  for (int kind = 0; kind < 2; ++kind) {
+    const size_t n_chunks = geos[kind]->size() / kSphereChunk;
+    ranges[kind].assign(n_chunks, Range { { inf, inf, inf }, { -inf, -inf, -inf }, false });
+    for (size_t i = 0; i < geos[kind]->size(); ++i) {
+      const SphereGeo& g = (*geos[kind])[i];
+      if (!g.valid) continue;
+      Range& rg = ranges[kind][i / kSphereChunk];
+      rg.any = true;
+      if ((*opens[kind])[i / kSphereChunk]) continue;
+      double f[2] = { 0, 0 };
+      if (g.time0 != g.time1) {
+        const double den = (double)(g.time1 - g.time0);  // the float the device divides by (sphere.hpp:55)
+        const double fa = (ct_lo - ct_pad - g.time0) / den, fb = (ct_hi + ct_pad - g.time0) / den;
+        const double pad = 1e-5 * (1.0 + std::max(std::fabs(fa), std::fabs(fb)));
+        f[0] = std::min(fa, fb) - pad, f[1] = std::max(fa, fb) + pad;
+        if (!(std::isfinite(f[0]) && std::isfinite(f[1]))) usable = false;
+        f_abs_max = std::max(f_abs_max, std::max(std::fabs(f[0]), std::fabs(f[1])));
+      }
+      const double r = std::fabs((double)g.radius);
+      r_min = std::min(r_min, r);
+      for (int end = 0; end < 2; ++end) {
+        double c[3], len2 = 0;
+        for (int k = 0; k < 3; ++k) {
+          const double dv = (double)(float)(g.c1[k] - g.c0[k]);  // the float the device multiplies by
+          c[k] = g.c0[k] + f[end] * dv;
+          len2 += c[k] * c[k];
+          rg.lo[k] = std::min(rg.lo[k], c[k] - r), rg.hi[k] = std::max(rg.hi[k], c[k] + r);
+        }
+        s_max = std::max(s_max, std::sqrt(len2) + r);
+      }
+    }
+  }
+  if (!(s_max > 0 && s_max < 1e12)) usable = false;
+  for (int k = 0; k < 3; ++k) out.bound[k] = 0.f;
+  double margin[kCullSets] = { inf, inf, inf, inf };
+  if (usable) {
+    const double mult[3] = { 2, 16, 128 };
+    for (int s = 0; s < 3; ++s) {
+      const double bound = mult[s] * s_max;
+      out.bound[s] = std::nextafter((float)bound, 0.f);
+      const double d = 1.7321 * bound + s_max;
+      const double e = 4e-6 * d * d;
+      const double m_geom = std::min(std::sqrt(e), r_min > 0 ? e / (2 * r_min) : inf);
+      margin[s] = 2 * m_geom + 1e-6 * (bound + s_max) * (2 + f_abs_max);
+    }
+  }
+  for (int kind = 0; kind < 2; ++kind) {
+    std::vector<float>& dst = kind ? out.moving : out.sphere;
+    const size_t n_chunks = ranges[kind].size();
+    dst.assign((size_t)kCullSets * n_chunks * 8, 0.f);
+    for (int s = 0; s < kCullSets; ++s)
+      for (size_t c = 0; c < n_chunks; ++c) {
+        float* b = dst.data() + ((size_t)s * n_chunks + c) * 8;
+        const Range& rg = ranges[kind][c];
+        const float finf = std::numeric_limits<float>::infinity();
+        bool open = (*opens[kind])[c] || !(margin[s] < inf);
+        for (int k = 0; k < 3 && !open; ++k)
+          if (!(std::fabs(rg.lo[k] - margin[s]) < 1e15 && std::fabs(rg.hi[k] + margin[s]) < 1e15)) open = true;
+        for (int k = 0; k < 3; ++k) {
+          if (!rg.any) {
+            b[k] = finf, b[4 + k] = -finf;  // nothing but padding: never scanned
+          } else if (open) {
+            b[k] = -finf, b[4 + k] = finf;
+          } else {
+            b[k] = std::nextafter((float)(rg.lo[k] - margin[s]), -finf);
+            b[4 + k] = std::nextafter((float)(rg.hi[k] + margin[s]), finf);
+          }
+        }
+      }
+  }
+}
 
 int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   out = PackedScene {};
@@ -154,6 +307,21 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   }
   auto mat_ok = [&](int32_t m) { return m >= 0 && (uint32_t)m < sc.n_materials; };
 
+  // Spheres far larger than the rest (a ground sphere of radius 1000 among marbles) would blow up the
+  // culling margins, which grow with the extent of what is culled: they go to chunks of their own
+  // that are always scanned.  "Far larger" = more than 4 x the median of |centre| + |radius|.
+  double outsized_above = std::numeric_limits<double>::infinity();
+  {
+    std::vector<double> ext;
+    for (uint32_t i = 0; i < sc.n_hittables; ++i)
+      if (sc.order[i].kind == PT_HIT_SPHERE && sc.order[i].index >= 0 && (uint32_t)sc.order[i].index < sc.n_spheres)
+        ext.push_back(sphere_extent(sc.spheres[sc.order[i].index]));
+    if (!ext.empty()) {
+      std::nth_element(ext.begin(), ext.begin() + (long)((ext.size() - 1) / 2), ext.end());
+      outsized_above = 4.0 * ext[(ext.size() - 1) / 2];
+    }
+  }
+
   Builder b(out);
   Segment seg;
   for (uint32_t i = 0; i < sc.n_hittables; ++i) {
@@ -165,29 +333,32 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
           return PT_ERR_INVALID_ARGUMENT;
         }
         const pt_sphere& s = sc.spheres[e.index];
-        SphereAux a {};
+        RawSphere rs {};
+        SphereAux& a = rs.aux;
         a.radius = s.radius, a.material = s.material, a.key = -1 - (int32_t)i;
         // The scan blob carries r*r inflated by the miss filter's margin, rounded up (pt_kernel.cu,
         // "conservative miss filter"); the exact r*r is recomputed from the side table's radius.
         const float r2_exact = s.radius * s.radius;
         const float r2 = std::nextafter(r2_exact * (1.0f + 2.0f * 4.0e-6f / (1.0f - 4.0e-6f)),
                                         std::numeric_limits<float>::infinity());
+        rs.head = f4 { s.center0[0], s.center0[1], s.center0[2], r2 };
+        rs.geo.radius = s.radius, rs.geo.time0 = s.time0, rs.geo.time1 = s.time1, rs.geo.valid = true;
+        for (int k = 0; k < 3; ++k) rs.geo.c0[k] = s.center0[k], rs.geo.c1[k] = s.center0[k];
+        rs.outsized = !(sphere_extent(s) <= outsized_above);
         if (s.time0 == s.time1) {  // sphere.hpp:52
-          seg.sph.push_back(f4 { s.center0[0], s.center0[1], s.center0[2], r2 });
-          seg.sph_aux.push_back(a);
+          seg.sph.push_back(rs);
         } else {
           MovingClass* cls = nullptr;
           for (auto& c : seg.classes)
             if (c.time0 == s.time0 && c.time1 == s.time1) cls = &c;
           if (!cls) {
-            seg.classes.push_back(MovingClass { s.time0, s.time1, {}, {} });
+            seg.classes.push_back(MovingClass { s.time0, s.time1, {} });
             cls = &seg.classes.back();
           }
           a.time0 = s.time0, a.den = s.time1 - s.time0;
-          cls->data.push_back(f4 { s.center0[0], s.center0[1], s.center0[2], r2 });
-          cls->data.push_back(f4 { s.center1[0] - s.center0[0], s.center1[1] - s.center0[1],
-                                   s.center1[2] - s.center0[2], 0.f });
-          cls->aux.push_back(a);
+          rs.dv = f4 { s.center1[0] - s.center0[0], s.center1[1] - s.center0[1], s.center1[2] - s.center0[2], 0.f };
+          for (int k = 0; k < 3; ++k) rs.geo.c1[k] = s.center1[k];
+          cls->items.push_back(rs);
         }
         break;
       }
@@ -293,6 +464,13 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   out.off_rect = append(out.blob, b.rect.data(), b.rect.size() * sizeof(f4));
   out.off_triangle = append(out.blob, b.tri.data(), b.tri.size() * sizeof(f4));
   out.off_box = append(out.blob, b.box.data(), b.box.size() * sizeof(f4));
+  {
+    // until compute_cull_boxes() has run for a camera, every chunk is scanned
+    CullBoxes none;
+    compute_cull_boxes(out, std::numeric_limits<float>::quiet_NaN(), std::numeric_limits<float>::quiet_NaN(), none);
+    out.off_sphere_box = append(out.blob, none.sphere.data(), none.sphere.size() * sizeof(float));
+    out.off_moving_box = append(out.blob, none.moving.data(), none.moving.size() * sizeof(float));
+  }
   while (out.blob.size() % 16 || out.blob.empty()) out.blob.push_back(0);
 
   out.materials.assign(sc.materials, sc.materials + sc.n_materials);

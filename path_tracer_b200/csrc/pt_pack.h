@@ -11,10 +11,20 @@
 
 namespace ptb {
 
+// What the chunk boxes are computed from (one per sphere ELEMENT, padding included).
+struct SphereGeo {
+  float c0[3], c1[3];
+  float radius, time0, time1;
+  bool valid;  // false: padding
+};
+
 struct PackedScene {
   std::vector<unsigned char> blob;
   uint32_t n_groups = 0;
   uint32_t off_groups = 0, off_sphere = 0, off_moving = 0, off_rect = 0, off_triangle = 0, off_box = 0;
+  uint32_t off_sphere_box = 0, off_moving_box = 0;  // [kCullSets][chunks][2] float4 each, "no culling" until set
+  std::vector<SphereGeo> sphere_geo, moving_geo;    // indexed like sphere_aux / moving_aux
+  std::vector<unsigned char> sphere_chunk_open, moving_chunk_open;  // 1: chunk is never culled (outsized spheres)
   uint32_t n_objects = 0;
   std::vector<SphereAux> sphere_aux, moving_aux;
   std::vector<ObjAux> rect_aux, box_aux;
@@ -23,6 +33,14 @@ struct PackedScene {
   std::vector<pt_material> materials;
   std::vector<pt_texture> textures;
 };
+
+// Chunk bounding boxes for a camera whose rays carry times in [cam_time0, cam_time1] (camera.hpp:97-99):
+// float4 {lo} {hi} per chunk, kCullSets sets per sphere kind, in the blob's layout.
+struct CullBoxes {
+  std::vector<float> sphere, moving;
+  float bound[3];
+};
+void compute_cull_boxes(const PackedScene& ps, float cam_time0, float cam_time1, CullBoxes& out);
 
 // Returns PT_OK or a PT_ERR_* code with a message in `error`.
 int pack_scene(const pt_scene& scene, PackedScene& out, std::string& error);

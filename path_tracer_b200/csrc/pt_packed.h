@@ -35,7 +35,7 @@
 namespace ptb {
 
 enum GroupType : int {
-  G_SPHERE = 0,         // static spheres: 1 float4 {cx, cy, cz, r*r}
+  G_SPHERE = 0,         // static spheres: 1 float4 {cx, cy, cz, r*r}, in CHUNKS (below)
   G_MOVING_SPHERE = 1,  // 2 float4 {c0x, c0y, c0z, r*r} {c1x-c0x, c1y-c0y, c1z-c0z, 0}; one (time0,time1) class
   G_RECT = 2,           // 2 float4 {a0, a1, b0, b1} {k, axis, 0, 0}
   G_TRIANGLE = 3,       // 3 float4 {v0, 0} {v1-v0, 0} {v2-v0, 0}
@@ -43,7 +43,18 @@ enum GroupType : int {
   G_MEDIUM = 5          // `begin` = index into the media table; closes a segment
 };
 
-constexpr int kSphereChunk = 32;  // static / moving sphere groups are padded to this many
+// Sphere groups are stored in CHUNKS of kSphereChunk spatially close spheres (k-d ordered by the packer,
+// padded with spheres that can never be hit).  Every chunk has a bounding box per origin class
+// (kCullSets of them, see "chunk culling" in pt_kernel.cu); a ray only scans the chunks whose box it
+// crosses, and lanes of a warp scan DIFFERENT chunks at the same time.  So that those loads do not
+// collide on shared-memory banks each lane starts at its own sphere of the chunk ((lane & 15) + j),
+// and so that this rotation needs no wrap-around arithmetic the 16 entries are stored TWICE in a row:
+//   static chunk c : float4[32] at 32 c      (entry s and its copy at 16 + s)
+//   moving chunk c : float4[64] at 64 c      ({c0, r*r} at s and 16 + s, {c1 - c0} at 32 + s and 48 + s)
+constexpr int kSphereChunk = 16;
+constexpr int kCullSets = 4;  // box sets per origin class; the last one is "no culling" (infinite boxes)
+PT_HD inline int sphere_slot(int i) { return ((i >> 4) << 5) | (i & 15); }  // float4 index of static sphere i
+PT_HD inline int moving_slot(int i) { return ((i >> 4) << 6) | (i & 15); }  // {c0, r*r}; {c1 - c0} is 32 further
 
 struct Group {  // 32 bytes
   int32_t type;
@@ -103,6 +114,10 @@ struct SceneDesc {
   uint32_t n_groups;
   uint32_t off_groups, off_sphere, off_moving, off_rect, off_triangle, off_box;
   uint32_t n_objects;         // reference n_hittables (for work accounting)
+  // chunk boxes: float4 {lo} {hi} per chunk, [kCullSets][n_chunks][2] per sphere kind; rewritten when the
+  // camera's shutter interval changes (the boxes of moving spheres cover their sweep over it)
+  uint32_t off_sphere_box, off_moving_box, n_sphere_chunks, n_moving_chunks;
+  float cull_bound[3];        // set s serves origins with max |coordinate| <= cull_bound[s]
   const SphereAux* sphere_aux;
   const SphereAux* moving_aux;
   const ObjAux* rect_aux;

@@ -3,12 +3,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, scenes
 from path_tracer_b200 import render as R
-# usage: timeline.py spp kernel(0 wave,1 lane) lpt(0/1) [express]
+# usage: timeline.py spp kernel(0 wave,1 lane) lpt(0/1) [express [team [cull]]]
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 L = R.lib()
 if len(sys.argv) > 2: L.pt_debug_set_kernel(int(sys.argv[2]))
 if len(sys.argv) > 3: L.pt_debug_set_lpt(int(sys.argv[3]))
 if len(sys.argv) > 4: L.pt_debug_set_express(int(sys.argv[4]))
+if len(sys.argv) > 5: L.pt_debug_set_team_size(int(sys.argv[5]))
+if len(sys.argv) > 6: L.pt_debug_set_cull(int(sys.argv[6]))
 sc, cam, (w, h, _, d) = scenes.load_c1()
 ds = R.DeviceScene(sc, 0)
 fb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
