@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -47,7 +48,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 constexpr int kCounterSlots = 64;
 constexpr unsigned kHeavyCap = 32768;  // entries of the heavy-pixel hand-off queue
-constexpr int kCounterWords = 8;  // [0] scans, [1] first CTA start (ns), [2] queue ran dry (ns), [3] last warp retired (ns)
+constexpr int kCounterWords = 24;  // [0] scans, [1] first CTA start (ns), [2] queue ran dry (ns), [3] last warp retired (ns)
 
 }  // namespace
 
@@ -171,6 +172,17 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   key_base[G_MEDIUM] = (uint32_t)keys.size();
   for (const auto& a : ps.media) keys.push_back(a.key);
   const size_t o_keys = place(host, keys);
+  // original object index -> scan id (a sphere's key is -1 - index, any other object's is the index, pt_packed.h)
+  std::vector<int32_t> object_id(std::max<uint32_t>(ps.n_objects, 1u), -1);
+  for (size_t i = 0; i < ps.rect_aux.size(); ++i) object_id[(size_t)ps.rect_aux[i].key] = make_id(G_RECT, (int)i);
+  for (size_t i = 0; i < ps.tri_aux.size(); ++i) object_id[(size_t)ps.tri_aux[i].key] = make_id(G_TRIANGLE, (int)i);
+  for (size_t i = 0; i < ps.box_aux.size(); ++i) object_id[(size_t)ps.box_aux[i].key] = make_id(G_BOX, (int)i);
+  for (size_t i = 0; i < ps.media.size(); ++i) object_id[(size_t)ps.media[i].key] = make_id(G_MEDIUM, (int)i);
+  for (size_t i = 0; i < ps.sphere_aux.size(); ++i)
+    if (ps.sphere_aux[i].material >= 0) object_id[(size_t)(-1 - ps.sphere_aux[i].key)] = make_id(G_SPHERE, (int)i);
+  for (size_t i = 0; i < ps.moving_aux.size(); ++i)
+    if (ps.moving_aux[i].material >= 0) object_id[(size_t)(-1 - ps.moving_aux[i].key)] = make_id(G_MOVING_SPHERE, (int)i);
+  const size_t o_objid = place(host, object_id);
   const size_t o_mat = place(host, ps.materials);
   const size_t o_tex = place(host, ps.textures);
   const size_t o_heads = align_up(host.size(), 256);
@@ -236,6 +248,8 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   d.n_texture_texels = tex_bytes / 3;
   d.n_materials = (uint32_t)ps.materials.size();
   d.n_textures = (uint32_t)ps.textures.size();
+  d.object_id = reinterpret_cast<const int32_t*>(ds->arena + o_objid);
+  d.n_media_groups = ps.n_media_groups, d.n_flat_groups = ps.n_flat_groups, d.n_late_sphere_groups = ps.n_late_sphere_groups;
   d.off_sphere_box = ps.off_sphere_box, d.off_moving_box = ps.off_moving_box;
   d.n_sphere_chunks = (uint32_t)ps.sphere_chunk_open.size(), d.n_moving_chunks = (uint32_t)ps.moving_chunk_open.size();
   d.cull_bound[0] = d.cull_bound[1] = d.cull_bound[2] = 0.f;  // no culling until update_chunk_boxes()
@@ -377,6 +391,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   PT_CUDA(cudaMemsetAsync(p.counters + 3, 0, 2 * sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 5, 0xff, sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 6, 0, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 8, 0, 16 * sizeof(unsigned long long), st));  // hand-off service statistics
 
   // Longest-processing-time-first pixel order (wavefront kernel, images worth it): a cost probe traces
   // ONE throw-away sample through every second pixel of every second row (1/(4 spp) of the frame's
@@ -470,16 +485,30 @@ int pt_debug_set_express(int n) {
 
 // Debug aid (not part of pt_abi.h): timeline of the LAST launch on this scene, in ns:
 // out[0] = queue-dry - start, out[1] = last-warp-retired - start.
-int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[5]) {
+// out[5..9]: hand-off service: rounds, ray-rounds, total and longest wait in the queue (ns), longest stay (rounds)
+int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[10]) {
   PT_CUDA(cudaSetDevice(scene->device));
   PT_CUDA(cudaDeviceSynchronize());
-  unsigned long long v[8];
+  unsigned long long v[16];
   PT_CUDA(cudaMemcpy(v, scene->counters, sizeof v, cudaMemcpyDeviceToHost));
   unsigned int ctrl[4];
   PT_CUDA(cudaMemcpy(ctrl, scene->heavy_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
   out[0] = v[2] - v[1], out[1] = v[3] - v[1];
   out[2] = v[5] - v[1], out[3] = v[6] - v[1];  // first / last CTA out of regular work
   out[4] = ctrl[1];                            // heavy pixels handed to the express lane
+  out[5] = v[8], out[6] = v[9], out[7] = v[12], out[8] = v[13], out[9] = v[14];
+  if (const char* env = std::getenv("PT_PHASE_TIMING")) {  // debug builds (-DPT_PHASE_TIMING): cycles per phase
+    (void)env;
+    std::fprintf(stderr, "desc: groups %u media %u flat %u sphere chunks %u moving chunks %u blob %u B\n", scene->desc.n_groups,
+                 scene->desc.n_media_groups, scene->desc.n_flat_groups, scene->desc.n_sphere_chunks, scene->desc.n_moving_chunks,
+                 scene->desc.blob_bytes);
+    unsigned long long ph[8];
+    PT_CUDA(cudaMemcpy(ph, scene->counters + 16, sizeof ph, cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "phase cycles per round: boxes %.0f spheres %.0f flat %.0f sort %.0f shade %.0f; %llu rounds, %.1f rays, %.1f items\n",
+                 (double)ph[0] / (double)std::max(ph[5], 1ull), (double)ph[1] / (double)std::max(ph[5], 1ull),
+                 (double)ph[2] / (double)std::max(ph[5], 1ull), (double)ph[3] / (double)std::max(ph[5], 1ull),
+                 (double)ph[4] / (double)std::max(ph[5], 1ull), ph[5], (double)ph[6] / (double)std::max(ph[5], 1ull), (double)ph[7] / (double)std::max(ph[5], 1ull));
+  }
   return PT_OK;
 }
 

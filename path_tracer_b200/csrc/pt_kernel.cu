@@ -414,18 +414,50 @@ template <bool kSmem> PT_DEV uint32_t chunk_bits(const float4* __restrict__ box,
   return __float_as_uint(t_in - t_out);
 }
 
-// Scan the chunks [first_el / 16, end_el / 16) of one sphere group for one ray.  Every lane first
-// collects the bitmask of chunks its ray crosses (same box for all lanes: broadcast loads), then
-// pops its OWN next chunk and filters its share of the 16 spheres, kTeam lanes per ray: own k-th
-// sphere = slot rot + k * kTeam of the doubled chunk, rot = lane & 15, so that the lanes of a warp,
-// each on a different chunk, read different shared-memory banks.
+// Bitmask of the chunks cb .. cb + nb - 1 (nb <= 32) whose box the ray crosses before tmax: chunk cb + k at
+// bit nb - 1 - k.  Same box for every lane: broadcast loads.
+template <bool kSmem>
+PT_DEV uint32_t chunk_hits(const float4* __restrict__ boxes, int cb, int nb, const CullRay& cr, float tmax) {
+  uint32_t hits = 0;
+#pragma unroll 2
+  for (int k = 0; k < nb; ++k) hits = __funnelshift_l(chunk_bits<kSmem>(boxes + 2 * (cb + k), cr, tmax), hits, 1);
+  return hits;
+}
+
+// Filter + exact roots of kOwn spheres of one chunk: slots p, p + kStep, ... of the doubled chunk, where
+// p = chunk base + rot0 (pt_packed.h).  Lanes of a warp work on DIFFERENT chunks at the same time; with
+// rot0 = (lane & 15) + const they read different shared-memory banks.
+template <bool kSmem, bool kMoving, int kOwn, int kStep, typename Keys>
+PT_DEV void scan_chunk(const Keys& sc, const float4* __restrict__ data, const SphereAux* aux, int chunk, int rot0,
+                       const Ray& r, float a, float af, float f, int type, Best& best) {
+  constexpr int kUnroll = kOwn < kScanUnroll ? kOwn : kScanUnroll;
+  constexpr int kSlots = kMoving ? 4 * kSphereChunk : 2 * kSphereChunk;  // float4 per chunk
+  const float4* base = data + chunk * kSlots + rot0;
+  uint32_t mask = 0;  // own k-th sphere at bit kOwn - 1 - k
+#pragma unroll 1
+  for (int it = 0; it < kOwn; it += kUnroll) {
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j)
+      mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(base + (it + j) * kStep, f, r, af), mask, 1);
+  }
+  while (mask) {
+    const int mt = 31 - __clz((int)mask);
+    mask &= ~(1u << mt);
+    const int k = kOwn - 1 - mt;
+    const int i = chunk * kSphereChunk + ((rot0 + k * kStep) & (kSphereChunk - 1));
+    float cx, cy, cz, r2f;
+    sphere_center<kSmem, kMoving>(base + k * kStep, f, cx, cy, cz, r2f);
+    sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
+  }
+}
+
+// Scan the chunks [first_el / 16, end_el / 16) of one sphere group for one ray, kTeam lanes per ray: every
+// lane first collects the bitmask of chunks the ray crosses, then pops its next chunk and filters its
+// share of the 16 spheres (own k-th sphere = slot rot + k * kTeam, rot = lane & 15).
 template <bool kSmem, bool kMoving, int kTeam, typename Keys>
 PT_DEV void scan_sphere_chunks(const Keys& sc, const float4* __restrict__ data, const float4* __restrict__ boxes,
                                const SphereAux* aux, int first_el, int end_el, int rot, const Ray& r, float a,
                                float f, const CullRay& cr, bool act, int type, Best& best) {
-  constexpr int kOwn = kSphereChunk / kTeam;
-  constexpr int kUnroll = kOwn < kScanUnroll ? kOwn : kScanUnroll;
-  constexpr int kSlots = kMoving ? 4 * kSphereChunk : 2 * kSphereChunk;  // float4 per chunk
   const float af = filter_a(a);
   const int c_end = end_el / kSphereChunk;
 #pragma unroll 1
@@ -434,8 +466,7 @@ PT_DEV void scan_sphere_chunks(const Keys& sc, const float4* __restrict__ data, 
     float tmax = act ? best.t : -1.f;
     uint32_t hits = 0;  // chunk cb + k at bit nb - 1 - k
     if constexpr (kTeam == 1) {
-#pragma unroll 2
-      for (int k = 0; k < nb; ++k) hits = __funnelshift_l(chunk_bits<kSmem>(boxes + 2 * (cb + k), cr, tmax), hits, 1);
+      hits = chunk_hits<kSmem>(boxes, cb, nb, cr, tmax);
     } else {
       // The team shares the box tests: member m takes chunks m, m + kTeam, ... against the smallest of the
       // members' running closest hits, and the members' bits are OR-ed together (the whole warp is
@@ -452,24 +483,7 @@ PT_DEV void scan_sphere_chunks(const Keys& sc, const float4* __restrict__ data, 
     while (hits) {
       const int top = 31 - __clz((int)hits);
       hits &= ~(1u << top);
-      const int chunk = cb + (nb - 1 - top);
-      const float4* base = data + chunk * kSlots + rot;
-      uint32_t mask = 0;  // own k-th sphere at bit kOwn - 1 - k
-#pragma unroll 1
-      for (int it = 0; it < kOwn; it += kUnroll) {
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j)
-          mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(base + (it + j) * kTeam, f, r, af), mask, 1);
-      }
-      while (mask) {
-        const int mt = 31 - __clz((int)mask);
-        mask &= ~(1u << mt);
-        const int k = kOwn - 1 - mt;
-        const int i = chunk * kSphereChunk + ((rot + k * kTeam) & (kSphereChunk - 1));
-        float cx, cy, cz, r2f;
-        sphere_center<kSmem, kMoving>(base + k * kTeam, f, cx, cy, cz, r2f);
-        sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
-      }
+      scan_chunk<kSmem, kMoving, kSphereChunk / kTeam, kTeam>(sc, data, aux, cb + (nb - 1 - top), rot, r, a, af, f, type, best);
     }
   }
 }
@@ -503,6 +517,40 @@ PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, c
                                              act, type, best);
 }
 
+// Rectangles, triangles and boxes of one group: elements first, first + step, ... (running closest as the
+// upper bound, like the reference's loop).
+template <bool kSmem>
+PT_DEV void scan_flat_group(const SceneDesc& sc, const SceneView& sv, const Group& g, const Ray& r, int first, int step,
+                            Best& best) {
+  const int end = g.begin + g.count;
+  if (g.type == G_RECT) {
+    for (int i = first; i < end; i += step) {
+      const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
+      const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
+      float t, ra, rb;
+      if (rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, best.t, t, ra, rb))
+        consider_le(sc, best, t, make_id(G_RECT, i));
+    }
+  } else if (g.type == G_TRIANGLE) {
+    for (int i = first; i < end; i += step) {
+      const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
+      const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
+      const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
+      float t;
+      if (triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, best.t, t))
+        consider_le(sc, best, t, make_id(G_TRIANGLE, i));
+    }
+  } else if (g.type == G_BOX) {
+    for (int i = first; i < end; i += step) {
+      const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
+      const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
+      float t, ra, rb;
+      if (box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, best.t, t, ra, rb) >= 0)
+        consider_le(sc, best, t, make_id(G_BOX, i));
+    }
+  }
+}
+
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
 // of each group.  `act`: this lane's team carries a real ray (the others ride along so that the
 // warp stays converged on the shared loads and the shuffles).
@@ -518,7 +566,7 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
   const int n_groups = (int)sc.n_groups;
   for (int gi = 0; gi < n_groups; ++gi) {
     const Group g = sv.groups[gi];
-    const int first = g.begin + member, end = g.begin + g.count;
+    const int end = g.begin + g.count;
     switch (g.type) {
       case G_SPHERE:
         scan_spheres<kSmem, false>(sc, sv.sphere, sphere_boxes, sc.sphere_aux, g.begin, end, team_size, r, a, 0.f, cr, act,
@@ -528,41 +576,7 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
         scan_spheres<kSmem, true>(sc, sv.moving, moving_boxes, sc.moving_aux, g.begin, end, team_size, r, a,
                                   fdiv(fsub(r.tm, g.time0), g.den), cr, act, G_MOVING_SPHERE, best);
         break;
-      case G_RECT: {
-        if (act)
-          for (int i = first; i < end; i += team_size) {
-            const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
-            const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
-            float t, ra, rb;
-            if (rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, best.t, t, ra, rb))
-              consider_le(sc, best, t, make_id(G_RECT, i));
-          }
-        break;
-      }
-      case G_TRIANGLE: {
-        if (act)
-          for (int i = first; i < end; i += team_size) {
-            const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
-            const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
-            const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
-            float t;
-            if (triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, best.t, t))
-              consider_le(sc, best, t, make_id(G_TRIANGLE, i));
-          }
-        break;
-      }
-      case G_BOX: {
-        if (act)
-          for (int i = first; i < end; i += team_size) {
-            const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
-            const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
-            float t, ra, rb;
-            if (box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, best.t, t, ra, rb) >= 0)
-              consider_le(sc, best, t, make_id(G_BOX, i));
-          }
-        break;
-      }
-      default: {
+      case G_MEDIUM: {
         // G_MEDIUM sees the running closest hit of EVERY lower-index object (merge first) and commits
         // unconditionally; every member replays the RNG draw on its replica of the generator.
         if (team_size > 1) team_merge(sc, best, team_size);
@@ -572,6 +586,9 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
         }
         break;
       }
+      default:
+        if (act) scan_flat_group<kSmem>(sc, sv, g, r, g.begin + member, team_size, best);
+        break;
     }
   }
   if (team_size > 1) team_merge(sc, best, team_size);
@@ -1045,26 +1062,37 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 // ---------------------------------------------------------------- the wavefront kernel
 // Bulk-synchronous wavefront inside one CTA per SM.  The path state of up to kWavePool pixels lives
 // in a structure-of-arrays RAY POOL in shared memory instead of in the registers of fixed lanes, and
-// the CTA alternates between three phases separated by __syncthreads():
+// the CTA alternates between phases separated by __syncthreads():
 //
-//   SCAN   every live ray gets its closest hit (render.hpp:30-51).  All warps run the same tight
-//          loops at the same time, so the loops own the instruction cache and the issue ports.
-//          With fewer live rays than lanes a ray is scanned by a TEAM of lanes (see closest_hit).
-//   SORT   the rays are counting-sorted by what has to happen next: background, or the kind of the
-//          hit material (the "compact divergent material work" step, done across the CTA).
-//   SHADE  batches of 32 CONSECUTIVE sorted rays are shaded by one warp each, so the lanes of a warp
-//          run the same material code; finished paths start their pixel's next sample (the RNG
-//          stream of a pixel is strictly serial) or write the pixel and pull a new one from the
-//          global pixel queue.
+//   BOXES   one thread per ray: which sphere chunks does the ray cross (chunk culling, above)?  Every
+//           (ray, chunk) pair becomes a work ITEM in a CTA-wide list.
+//   SPHERES one thread per ITEM: the 16 spheres of the chunk against the ray; a hit is merged into the
+//           ray's winner with one 64-bit shared-memory atomicMin on {t, original object index} -- exactly
+//           the reference's rule for spheres (smallest t, then the earlier object, sphere.hpp:77,93).
+//           The work per item is the same whatever the ray, so the lanes of a warp stay busy although
+//           their rays cross different numbers of chunks, and a CTA with few rays left still has
+//           (rays x chunks) items to spread over its threads.
+//   FLAT    one thread per ray: rectangles, triangles, boxes and constant_media in object order against
+//           the running closest hit, then what has to happen next: background, or the kind of the hit
+//           material.
+//   SORT    the rays are counting-sorted by that kind ("compact divergent material work").
+//   SHADE   batches of 32 CONSECUTIVE sorted rays are shaded by one warp each, so the lanes of a warp
+//           run the same material code; finished paths start their pixel's next sample (the RNG
+//           stream of a pixel is strictly serial) or write the pixel and pull a new one from the
+//           global pixel queue.
+// A scene with spheres BEHIND a constant_medium in the object list is scanned sequentially per ray in
+// BOXES instead (the medium needs the running closest hit of everything before it, and what follows
+// needs the medium's).
 //
 // HAND-OFF QUEUE.  A pixel's samples are serial and a full round takes tens of microseconds, so the
 // few pixels that hold ten times the average work (paths bouncing dozens of times inside glass:
 // 3 000 scans where the mean is 260) would sit on a critical path longer than the whole frame, and
 // at the end of the frame every CTA would drain its own leftovers alone.  A pixel whose scan rate
 // marks it as HEAVY is therefore handed, with its complete path state, to a global queue.  It is
-// taken over by a CTA that runs SHORT rounds: one of a few EXPRESS CTAs that keep only a handful of
-// rays in flight (each scanned by a team of lanes, a round of a few microseconds), or any CTA whose
-// own pixels have run out -- which also balances the end of the frame across the whole GPU.
+// taken over by a CTA that runs SHORT rounds because it keeps only kExpressPool rays in flight: one
+// of a few EXPRESS CTAs that do nothing else, or any CTA whose own pixels have run out -- which also
+// balances the end of the frame across the whole GPU.  With few rays the phases switch to finer
+// work units (a ray's boxes in blocks of 8, a chunk's spheres in quarters).
 //
 // Results are bit-identical to the lane kernel: the same device functions are called on the same
 // per-pixel state, only the assignment of work to lanes differs.
@@ -1086,15 +1114,37 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 #ifndef PT_EXPRESS_TEAM
 #define PT_EXPRESS_TEAM 16
 #endif
+#ifndef PT_EXPRESS_POOL
+#define PT_EXPRESS_POOL 64
+#endif
+#ifndef PT_WAVE_ITEMS
+#define PT_WAVE_ITEMS 12288
+#endif
 constexpr int kWaveThreads = PT_WAVE_THREADS;
 constexpr int kWavePool = PT_WAVE_ROUNDS * kWaveThreads;  // pixels (rays) a CTA keeps in flight: whole scan passes
 constexpr int kWaveKinds = 6;                              // 0 = background, 1 + PT_MAT_* otherwise
 constexpr int kHeavyRate = PT_HEAVY_RATE;                  // heavy: more than kHeavyBase + rate * samples scans so far
 constexpr int kHeavyRateDry = PT_HEAVY_RATE_DRY;           // ... a lower bar once the pixel queue is dry (load sharing)
 constexpr int kHeavyBase = 64;
-constexpr int kExpressTeam = PT_EXPRESS_TEAM;              // lanes per handed-off pixel in the express service
+constexpr int kExpressTeam = PT_EXPRESS_TEAM;              // lane kernel's express service (unused by the wavefront kernel)
+constexpr int kExpressPool = PT_EXPRESS_POOL;              // rays in flight in a CTA that serves the hand-off queue
+constexpr int kWaveItems = PT_WAVE_ITEMS;                  // (ray, chunk) items per round; the overflow is scanned in place
+constexpr int kWaveItemsStatic = kWaveItems * 3 / 8;       // ... of static spheres (from the front of the list)
+constexpr int kWaveItemsMoving = kWaveItems - kWaveItemsStatic;  // ... of moving spheres (from the back)
+constexpr unsigned long long kNoHit64 = 0x7f800000ffffffffull;  // {t = +inf, no object}
+#ifndef PT_FINE_RAYS
+#define PT_FINE_RAYS 160
+#endif
+constexpr int kFineRays = PT_FINE_RAYS;  // at most this many rays in the round: finer work units (short rounds)
+constexpr int kFineBoxes = 8;            // ... BOXES: a ray's chunks in blocks of this many
+constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in runs of this many
+constexpr int kMaxBoxBlocks = 64;
+constexpr int kMaxFlats = 256;
+static_assert(kWavePool <= 1024, "an item packs the pool slot into 10 bits");
 
 struct WavePool {
+  unsigned long long best64[kWavePool];  // SPHERES: {float bits of t, original object index} of the ray's winner
+  uint2 items[kWaveItems];               // {slot | chunk << 10, f bits}: static-sphere items from the front, moving from the back
   float ox[kWavePool], oy[kWavePool], oz[kWavePool], dx[kWavePool], dy[kWavePool], dz[kWavePool], tm[kWavePool];
   float hit_t[kWavePool];
   int hit_id[kWavePool];
@@ -1107,17 +1157,21 @@ struct WavePool {
   int scans[kWavePool];               // closest-hit scans spent on the current pixel (< 0: taken over, never handed off again)
   unsigned short list_a[kWavePool];   // rays to scan (unordered)
   unsigned short list_b[kWavePool];   // the same rays sorted by kind
-  unsigned short free_list[kWavePool];
+  unsigned short free_list[kWavePool];  // hand-off service: pool slots without a pixel
   unsigned char kind[kWavePool];
   int counts[8];
   int cursor[8];
   int n_next;      // length of list_a being built
   int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
+  int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
   int free_count;
   int pixel_dry;   // the pixel queue has run dry
-  // per-round snapshot of the global queues, taken by thread 0 so that every thread decides alike
-  unsigned int snap_head, snap_tail, snap_done, snap_timeout;
-  unsigned long long snap_consumed;
+  int service;     // hand-off service: 0 = keep polling, 1 = every producer is done and the queue is empty
+  int n_blocks;    // fine BOXES: blocks of <= kFineBoxes chunks over all sphere groups (0: too many, coarse only)
+  int4 blocks[kMaxBoxBlocks];  // {group, first chunk, chunks, 0}
+  int n_flats;     // rectangles, triangles and boxes in FRONT of the first constant_medium: tested one thread per (ray, object)
+  int first_late_group;  // the first constant_medium's group (n_groups if none): from here on the scan is sequential per ray
+  int2 flats[kMaxFlats];  // {group type, element}
 };
 
 PT_DEV int material_of(const SceneDesc& sc, int id) {
@@ -1130,6 +1184,23 @@ PT_DEV int material_of(const SceneDesc& sc, int id) {
     case G_BOX: return sc.box_aux[idx].material;
     default: return sc.media[idx].material;
   }
+}
+
+// A ray's winner as one 64-bit word whose UNSIGNED ORDER is the winner rule of pt_packed.h (smaller t, then larger
+// key): {float bits of t (t >= 0), 0x7fffffff - key}.  Spheres (key = -1 - object) give codes 0x80000000 + object,
+// the others (key = object) 0x7fffffff - object.  A NaN t orders behind +inf and is never taken.
+PT_DEV unsigned long long pack_winner(float t, int key) {
+  return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(0x7fffffffu - (uint32_t)key);
+}
+PT_DEV unsigned long long pack_sphere_winner(const SphereAux* aux, const Best& b) {
+  return pack_winner(b.t, aux[b.id & (int)kIdMask].key);
+}
+PT_DEV Best unpack_winner(const SceneDesc& sc, unsigned long long v) {
+  Best best;
+  const uint32_t code = (uint32_t)v;
+  best.t = __uint_as_float((uint32_t)(v >> 32));
+  best.id = code == 0xffffffffu ? -1 : sc.object_id[code >= 0x80000000u ? code - 0x80000000u : 0x7fffffffu - code];
+  return best;
 }
 
 template <bool kSmem>
@@ -1164,13 +1235,16 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
+  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rot = lane & (kSphereChunk - 1);
   const pt_camera& cam = p.cam;
   const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
   const unsigned lane_lt = (1u << lane) - 1u;
   const HeavyQueue& hq = p.heavy;
   const bool express = (int)blockIdx.x < p.n_express;  // this CTA only serves the hand-off queue
-  const int own_cap = p.pool_cap;
+  const bool sequential_scan = sc.n_late_sphere_groups != 0u;
+  const int n_groups = (int)sc.n_groups;
   unsigned int n_scans = 0;
 
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
@@ -1192,6 +1266,28 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       return true;
     }
   };
+  // Take the next entry of the hand-off queue: its index, or -1 when there is none right now.
+  auto take_heavy = [&]() -> int {
+    unsigned int h = ld_volatile_u32(hq.ctrl + 0);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+      const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
+      if (h >= t) return -1;
+      const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
+      if (seen == h) {
+        while (ld_volatile_u32(hq.ready + h) != hq.stamp) {
+          if (globaltimer_ns() > t_give_up) {
+            if (p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
+            return -1;
+          }
+          __nanosleep(100);
+        }
+        __threadfence();
+        return (int)h;
+      }
+      h = seen;
+    }
+    return -1;
+  };
   // Append the live slots of this warp to the next scan list (one shared-memory atomic per warp).
   auto append = [&](bool alive, bool own, int slot) {
     const unsigned m = __ballot_sync(0xffffffffu, alive);
@@ -1212,106 +1308,349 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     W.att_x[slot] = att.x, W.att_y[slot] = att.y, W.att_z[slot] = att.z;
     W.acc_x[slot] = acc.x, W.acc_y[slot] = acc.y, W.acc_z[slot] = acc.z;
     W.rng[slot] = rng.s, W.bounce[slot] = bounce, W.sample[slot] = sample;
+    W.best64[slot] = kNoHit64;
+  };
+  auto load_ray = [&](int slot) -> Ray {
+    Ray ray;
+    ray.o = v3(W.ox[slot], W.oy[slot], W.oz[slot]);
+    ray.d = v3(W.dx[slot], W.dy[slot], W.dz[slot]);
+    ray.tm = W.tm[slot];
+    return ray;
+  };
+  // BOXES for one ray and the chunks [cb, cb + nb) of one sphere group: every crossed chunk becomes an item;
+  // what does not fit into the item list is scanned here and now (`inl`).
+  auto emit_items = [&](int slot, const Ray& ray, const CullRay& cr, const float4* boxes, bool moving, int cb, int nb, float f,
+                        float a, Best& inl) {
+    uint32_t hits = chunk_hits<kSmem>(boxes, cb, nb, cr, kInf);
+    if (hits == 0u) return;
+    const int cnt = __popc(hits);
+    int at = atomicAdd(moving ? &W.n_items_m : &W.n_items_s, cnt);
+    // static items grow from the front, moving ones from the back, each within its fixed share of the list
+    while (hits) {
+      const int top = 31 - __clz((int)hits);
+      hits &= ~(1u << top);
+      const int chunk = cb + (nb - 1 - top);
+      if (at < (moving ? kWaveItemsMoving : kWaveItemsStatic)) {
+        W.items[moving ? kWaveItems - 1 - at : at] = make_uint2((uint32_t)slot | ((uint32_t)chunk << 10), __float_as_uint(f));
+      } else if (moving) {
+        scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
+      } else {
+        scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
+      }
+      ++at;
+    }
   };
 
-  if (!express) {
-  // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
-  if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
-  if (tid == 0) W.n_next = 0, W.n_own = 0, W.free_count = 0, W.pixel_dry = 0;
-  __syncthreads();
-  for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
-    const int slot = s0 + lane;
-    bool alive = false;
-    if (slot < own_cap) {
-      uint32_t pixq;
-      Rng rng;
-      int px, py;
-      if (next_pixel(pixq, rng, px, py)) {
-        Ray ray;
-        camera_ray(cam, px, py, fwidth, fheight, rng, ray);
-        store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
-        W.pix[slot] = pixq, W.scans[slot] = 0;
-        alive = true;
+  int mode = 0;  // 0: this CTA's share of the pixel queue (none for an express CTA); 1: hand-off service
+  if (tid == 0) {
+    int nb = 0;
+    for (int gi = 0; gi < n_groups && nb >= 0; ++gi) {
+      const Group g = sv.groups[gi];
+      if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
+      const int c_end = (g.begin + g.count) / kSphereChunk;
+      for (int cb = g.begin / kSphereChunk; cb < c_end; cb += kFineBoxes) {
+        if (nb == kMaxBoxBlocks) {
+          nb = -1;
+          break;
+        }
+        W.blocks[nb++] = make_int4(gi, cb, min(kFineBoxes, c_end - cb), 0);
       }
     }
-    if (!alive) W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;
-    append(alive, true, slot);
+    W.n_blocks = nb < 0 ? 0 : nb;
+    // the flat objects in front of the first medium (as many as fit; the rest stays with the sequential part)
+    int nf = 0, late = n_groups;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const Group g = sv.groups[gi];
+      if (g.type == G_MEDIUM || ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && nf + g.count > kMaxFlats)) {
+        late = gi;
+        break;
+      }
+      if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX)
+        for (int i = 0; i < g.count; ++i) W.flats[nf++] = make_int2(g.type, g.begin + i);
+    }
+    W.n_flats = nf, W.first_late_group = late;
   }
+  if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
+  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
+  if (!express) {
+    // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
+    for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
+      const int slot = s0 + lane;
+      bool alive = false;
+      if (slot < p.pool_cap) {
+        uint32_t pixq;
+        Rng rng;
+        int px, py;
+        if (next_pixel(pixq, rng, px, py)) {
+          Ray ray;
+          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+          W.pix[slot] = pixq, W.scans[slot] = 0;
+          alive = true;
+        }
+      }
+      append(alive, true, slot);
+    }
+    __syncthreads();
+  }
 
-  // ---- rounds of SCAN / SORT / SHADE until this CTA's own pixels are finished
-  for (;;) {
-    const int n = W.n_next;  // rays to trace this round
-    if (n == 0) break;
-
-    // ---- SCAN: choose lanes per ray so that the CTA's lanes are used best
-    int team_size = 1, passes = (n + kWaveThreads - 1) / kWaveThreads;
-    {
-      float best_cost = (float)passes * 1.0f;
-      for (int t = 2, lg = 1; t <= kSphereChunk; t <<= 1, ++lg) {
-        const int ps = (n * t + kWaveThreads - 1) / kWaveThreads;
-        const float cost = (float)ps * (1.15f / (float)t + 0.03f * (float)lg);
-        if (cost < best_cost) best_cost = cost, team_size = t, passes = ps;
+  for (unsigned int round = 0;; ++round) {
+    if (mode == 1) {
+      // ---- hand-off service: fill the free pool slots from the global queue (polled every 4th round:
+      // a poll is a round trip to L2)
+      const int room = W.free_count, waiting = W.n_next;
+      __syncthreads();  // everybody has read the two before anybody changes them
+      if (room > 0 && ((round & 3u) == 0u || waiting == 0)) {
+        int got = -1;
+        if (tid < room) got = take_heavy();
+        if (got >= 0) {
+          const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
+          const float* e = hq.entries + (size_t)got * kHeavyEntryWords;
+          Ray ray;
+          ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
+          ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
+          ray.tm = __ldcg(e + 10);
+          store_ray(slot, ray, v3(__ldcg(e + 11), __ldcg(e + 12), __ldcg(e + 13)), v3(__ldcg(e + 14), __ldcg(e + 15), __ldcg(e + 16)),
+                    Rng { __float_as_uint(__ldcg(e + 1)) }, __float_as_int(__ldcg(e + 3)), __float_as_int(__ldcg(e + 2)));
+          W.pix[slot] = __float_as_uint(__ldcg(e + 0)), W.scans[slot] = -1;
+          W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
+          if (p.counters) {  // stats: how long did the pixel wait in the queue
+            const unsigned long long waited = (uint32_t)((uint32_t)globaltimer_ns() - __float_as_uint(__ldcg(e + 17)));
+            atomicAdd(p.counters + 12, waited), atomicMax(p.counters + 13, waited);
+          }
+        }
+        __syncthreads();
       }
     }
-    const int member = tid & (team_size - 1);
-    const int rays_per_pass = kWaveThreads / team_size;
-    for (int pass = 0; pass < passes; ++pass) {
-      const int entry = pass * rays_per_pass + tid / team_size;
-      const bool act = entry < n;
-      const int slot = act ? (int)W.list_a[entry] : 0;
-      Ray ray;
-      ray.o = v3(W.ox[slot], W.oy[slot], W.oz[slot]);
-      ray.d = v3(W.dx[slot], W.dy[slot], W.dz[slot]);
-      ray.tm = W.tm[slot];
-      Rng rng { W.rng[slot] };
-      if (!act) ray.d = v3(0.f, 0.f, 0.f);
-      const Best best = closest_hit<kSmem>(sc, sv, ray, rng, act, member, team_size);
-      if (act && member == 0) {
+    const int n = W.n_next;  // rays to trace this round
+    if (n == 0) {
+      if (mode == 0) {
+        // ---- no regular work (left): say so, then serve the hand-off queue until the whole GPU is finished
+        if (p.order_mode == 2) break;  // the cost probe hands nothing off
+        mode = 1;
+        for (int s = tid; s < kExpressPool; s += kWaveThreads) W.free_list[s] = (unsigned short)s;
+        if (tid == 0) {
+          W.free_count = kExpressPool;
+          __threadfence();
+          atomicAdd(hq.ctrl + 2, 1u);
+          if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
+        }
+        __syncthreads();
+        continue;
+      }
+      // idle: every producer is done and the queue is empty (or the watchdog fired) => nothing will ever arrive again
+      if (tid == 0)
+        W.service = ((ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
+                      ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap)) ||
+                     globaltimer_ns() > t_give_up)
+                        ? 1
+                        : 0;
+      __syncthreads();
+      if (W.service == 1) break;
+      __nanosleep(300);
+      continue;  // (the next write of W.service is behind the barrier at the loop top)
+    }
+    const bool fine = n <= kFineRays && W.n_blocks > 0;
+#ifdef PT_PHASE_TIMING
+    long long pt_t0 = clock64();
+#define PT_PHASE(k)                                                                                   \
+  if (tid == 0 && p.counters) {                                                                       \
+    const long long now = clock64();                                                                  \
+    atomicAdd(p.counters + 16 + (k), (unsigned long long)(now - pt_t0));                              \
+    pt_t0 = now;                                                                                      \
+  }
+#else
+#define PT_PHASE(k)
+#endif
+    if (mode == 1 && tid == 0 && p.counters) atomicAdd(p.counters + 8, 1ull), atomicAdd(p.counters + 9, (unsigned long long)n);  // stats
+
+    // ---- BOXES (or, with media in the scene, the whole sequential scan)
+    if (sequential_scan) {
+      for (int e = tid; e < n; e += kWaveThreads) {
+        const int slot = (int)W.list_a[e];
+        const Ray ray = load_ray(slot);
+        Rng rng { W.rng[slot] };
+        const Best best = closest_hit<kSmem>(sc, sv, ray, rng, true, 0, 1);
         W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
         W.rng[slot] = rng.s;  // a constant_medium may have drawn from it (constant_medium.hpp:65)
-        if (W.scans[slot] >= 0) W.scans[slot] += 1;
-        int kind = 0;
-        if (best.id >= 0) kind = 1 + reinterpret_cast<const pt_material*>(sc.materials)[material_of(sc, best.id)].kind;
-        W.kind[slot] = (unsigned char)kind;
-        atomicAdd(&W.counts[kind], 1);
-        ++n_scans;
+      }
+    } else {
+      // one work unit = one ray x (all its chunks | a block of kFineBoxes chunks)
+      const int n_units = fine ? n * W.n_blocks : n;
+      for (int w = tid; w < n_units; w += kWaveThreads) {
+        const int e = fine ? w / W.n_blocks : w;
+        const int slot = (int)W.list_a[e];
+        const Ray ray = load_ray(slot);
+        CullRay cr;
+        const int cull_set = make_cull_ray(sc, ray, cr);
+        const float a = vdot(ray.d, ray.d);  // sphere.hpp:69
+        Best inl { kInf, -1 };
+        unsigned long long v = kNoHit64;
+        const int4 blk = fine ? W.blocks[w - e * W.n_blocks] : make_int4(0, 0, 0, 0);
+        for (int gi = fine ? blk.x : 0; gi < (fine ? blk.x + 1 : n_groups); ++gi) {
+          const Group g = sv.groups[gi];
+          if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
+          const bool moving = g.type == G_MOVING_SPHERE;
+          const float4* boxes = moving ? sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks
+                                       : sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
+          const float f = moving ? fdiv(fsub(ray.tm, g.time0), g.den) : 0.f;
+          const int c_first = fine ? blk.y : g.begin / kSphereChunk;
+          const int c_end = fine ? blk.y + blk.z : (g.begin + g.count) / kSphereChunk;
+          for (int cb = c_first; cb < c_end; cb += 32) {
+            emit_items(slot, ray, cr, boxes, moving, cb, min(32, c_end - cb), f, a, inl);
+            if (inl.id >= 0) {  // scanned in place: fold into the ray's winner
+              const unsigned long long w64 = pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, inl);
+              if (w64 < v) v = w64;
+              inl.t = kInf, inl.id = -1;
+            }
+          }
+        }
+        if (v != kNoHit64) atomicMin(&W.best64[slot], v);
       }
     }
     __syncthreads();
+    PT_PHASE(0)
+
+    // ---- SPHERES: one thread per (ray, chunk) item, or per quarter of one
+    if (!sequential_scan) {
+      const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving);
+#ifdef PT_PHASE_TIMING
+      if (tid == 0 && p.counters) atomicAdd(p.counters + 23, (unsigned long long)(n_s + n_m));
+#endif
+      if (!fine) {
+        for (int i = tid; i < n_s; i += kWaveThreads) {
+          const uint2 it = W.items[i];
+          const int slot = (int)(it.x & 1023u);
+          const Ray ray = load_ray(slot);
+          const float a = vdot(ray.d, ray.d);
+          Best b { kInf, -1 };
+          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
+                                                    G_SPHERE, b);
+          if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(sc.sphere_aux, b));
+        }
+        for (int i = tid; i < n_m; i += kWaveThreads) {
+          const uint2 it = W.items[kWaveItems - 1 - i];
+          const int slot = (int)(it.x & 1023u);
+          const Ray ray = load_ray(slot);
+          const float a = vdot(ray.d, ray.d);
+          Best b { kInf, -1 };
+          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                   __uint_as_float(it.y), G_MOVING_SPHERE, b);
+          if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(sc.moving_aux, b));
+        }
+      } else {
+        // the kParts threads of an item are neighbouring lanes: lane & 15 = 4 m + q takes slots 4 m + q + 4 k (like a team of 4)
+        constexpr int kParts = kSphereChunk / kFineQuarter;
+        static_assert(kWaveThreads % kParts == 0 && kParts == 4, "an item's threads must be lanes 4 m .. 4 m + 3");
+        for (int w = tid; w < kParts * (n_s + n_m); w += kWaveThreads) {
+          const int i = w / kParts;
+          const bool moving = i >= n_s;
+          const uint2 it = W.items[moving ? kWaveItems - 1 - (i - n_s) : i];
+          const int slot = (int)(it.x & 1023u);
+          const Ray ray = load_ray(slot);
+          const float a = vdot(ray.d, ray.d);
+          Best b { kInf, -1 };
+          if (moving)
+            scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                          __uint_as_float(it.y), G_MOVING_SPHERE, b);
+          else
+            scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                           0.f, G_SPHERE, b);
+          if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
+        }
+      }
+      // ... and one thread per (ray, flat object) for the rectangles, triangles and boxes in front of the first medium
+      const int n_flats = W.n_flats;
+      for (int w = tid; w < n * n_flats; w += kWaveThreads) {
+        const int j = w / n;  // object-major: the lanes of a warp test the same object (kind)
+        const int2 fo = W.flats[j];
+        const int slot = (int)W.list_a[w - j * n];
+        const Ray ray = load_ray(slot);
+        Group g {};
+        g.type = fo.x, g.begin = fo.y, g.count = 1;
+        Best b { kInf, -1 };
+        scan_flat_group<kSmem>(sc, sv, g, ray, fo.y, 1, b);
+        if (b.id >= 0) atomicMin(&W.best64[slot], pack_winner(b.t, key_of(sc, b.id)));
+      }
+      __syncthreads();
+    }
+    PT_PHASE(1)
+
+    // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
+    for (int e = tid; e < n; e += kWaveThreads) {
+      const int slot = (int)W.list_a[e];
+      Best best;
+      if (sequential_scan) {
+        best.t = W.hit_t[slot], best.id = W.hit_id[slot];
+      } else {
+        best = unpack_winner(sc, W.best64[slot]);
+        const int late = W.first_late_group;
+        if (late < n_groups) {
+          // from the first constant_medium on, in group order against the running closest hit; a medium commits
+          // unconditionally and may draw from the pixel's stream (constant_medium.hpp:52-65)
+          const Ray ray = load_ray(slot);
+          Rng rng { W.rng[slot] };
+          for (int gi = late; gi < n_groups; ++gi) {
+            const Group g = sv.groups[gi];
+            if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) {
+              scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, best);
+            } else if (g.type == G_MEDIUM) {
+              float t;
+              if (medium_hit_t(sc.media[g.begin], ray, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
+            }
+          }
+          W.rng[slot] = rng.s;
+        }
+        W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
+      }
+      W.scans[slot] += W.scans[slot] >= 0 ? 1 : -1;  // (a taken-over pixel counts downwards: -1 - rounds in the service)
+      int kind = 0;
+      if (best.id >= 0) kind = 1 + reinterpret_cast<const pt_material*>(sc.materials)[material_of(sc, best.id)].kind;
+      W.kind[slot] = (unsigned char)kind;
+      atomicAdd(&W.counts[kind], 1);
+      ++n_scans;
+    }
+    __syncthreads();
+    PT_PHASE(2)
 
     // ---- SORT by kind (counting sort; the order inside a kind does not matter)
+    int kind_base[kWaveKinds + 1], unit_base[kWaveKinds + 1];  // rays / 32-ray shading units in front of each kind
     {
-      int base[kWaveKinds];
-      int run = 0;
+      int run = 0, units = 0;
 #pragma unroll
-      for (int k = 0; k < kWaveKinds; ++k) base[k] = run, run += W.counts[k];
+      for (int k = 0; k < kWaveKinds; ++k) {
+        kind_base[k] = run, unit_base[k] = units;
+        run += W.counts[k], units += (W.counts[k] + 31) >> 5;
+      }
+      kind_base[kWaveKinds] = run, unit_base[kWaveKinds] = units;
       for (int e = tid; e < n; e += kWaveThreads) {
         const int slot = (int)W.list_a[e];
         const int k = (int)W.kind[slot];
         int b = 0;
 #pragma unroll
         for (int q = 0; q < kWaveKinds; ++q)
-          if (q == k) b = base[q];
+          if (q == k) b = kind_base[q];
         W.list_b[b + atomicAdd(&W.cursor[k], 1)] = (unsigned short)slot;
       }
-      if (tid == 0) W.n_next = 0, W.n_own = 0;
+      if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0;
     }
     __syncthreads();
+    PT_PHASE(3)
 
-    // ---- SHADE: one warp per batch of 32 consecutive sorted rays
+    // ---- SHADE: one warp per unit of up to 32 consecutive sorted rays of ONE kind (no divergence on the material)
     if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
     const int heavy_rate = W.pixel_dry ? kHeavyRateDry : kHeavyRate;
-    for (int e0 = warp * 32; e0 < n; e0 += kWaveThreads) {
-      const int e = e0 + lane;
-      const bool act = e < n;
+    for (int u = warp; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
+      int e = 0, e_end = 0;
+#pragma unroll
+      for (int k = 0; k < kWaveKinds; ++k)
+        if (u >= unit_base[k] && u < unit_base[k + 1]) e = kind_base[k] + ((u - unit_base[k]) << 5) + lane, e_end = kind_base[k + 1];
+      const bool act = e < e_end;
       const int slot = act ? (int)W.list_b[e] : 0;
       bool alive = false, own = false;
       if (act) {
-        Ray ray;
-        ray.o = v3(W.ox[slot], W.oy[slot], W.oz[slot]);
-        ray.d = v3(W.dx[slot], W.dy[slot], W.dz[slot]);
-        ray.tm = W.tm[slot];
+        Ray ray = load_ray(slot);
         const Best best { W.hit_t[slot], W.hit_id[slot] };
         V3 att = v3(W.att_x[slot], W.att_y[slot], W.att_z[slot]);
         V3 acc = v3(W.acc_x[slot], W.acc_y[slot], W.acc_z[slot]);
@@ -1355,14 +1694,16 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             __stcg(q + 7, ray.d.x), __stcg(q + 8, ray.d.y), __stcg(q + 9, ray.d.z), __stcg(q + 10, ray.tm);
             __stcg(q + 11, att.x), __stcg(q + 12, att.y), __stcg(q + 13, att.z);
             __stcg(q + 14, acc.x), __stcg(q + 15, acc.y), __stcg(q + 16, acc.z);
+            __stcg(q + 17, __uint_as_float((uint32_t)globaltimer_ns()));
             __threadfence();
             *reinterpret_cast<volatile unsigned int*>(hq.ready + i) = hq.stamp;
             new_pixel = true;
           }
         }
         if (new_pixel) {
+          if (!own && p.counters) atomicMax(p.counters + 14, (unsigned long long)(-1 - scans));  // stats: longest stay in the service
           int px, py;
-          alive = !express && next_pixel(pixq, rng, px, py);
+          alive = mode == 0 && next_pixel(pixq, rng, px, py);
           if (alive) {
             camera_ray(cam, px, py, fwidth, fheight, rng, ray);
             att = v3(1.f, 1.f, 1.f);
@@ -1370,8 +1711,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             bounce = 0, sample = 0;
             W.pix[slot] = pixq, W.scans[slot] = 0;
             own = true;
-          } else {
-            W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;
+          } else if (mode == 1) {
+            W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;  // refilled from the hand-off queue
           }
         }
         if (alive) store_ray(slot, ray, att, acc, rng, bounce, sample);
@@ -1379,16 +1720,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       append(alive, own, slot);
     }
     __syncthreads();
+    PT_PHASE(4)
+#ifdef PT_PHASE_TIMING
+    if (tid == 0 && p.counters) atomicAdd(p.counters + 21, 1ull), atomicAdd(p.counters + 22, (unsigned long long)n);
+#endif
   }
-  }  // regular CTA
-
-  // ---- no regular work (left): say so, then serve the hand-off queue until the whole GPU is finished
-  if (tid == 0) {
-    __threadfence();
-    atomicAdd(hq.ctrl + 2, 1u);
-    if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
-  }
-  lane_loop<kSmem, true>(p, sc, sv, kExpressTeam, n_scans);
 
   if (p.counters && lane == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   unsigned int warp_scans = n_scans;

@@ -457,6 +457,11 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   }
 
   out.n_groups = (uint32_t)b.groups.size();
+  for (const Group& g : b.groups) {
+    if ((g.type == G_SPHERE || g.type == G_MOVING_SPHERE) && out.n_media_groups != 0) ++out.n_late_sphere_groups;
+    if (g.type == G_MEDIUM) ++out.n_media_groups;
+    if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) ++out.n_flat_groups;
+  }
   out.n_objects = sc.n_hittables;
   out.off_groups = append(out.blob, b.groups.data(), b.groups.size() * sizeof(Group));
   out.off_sphere = append(out.blob, b.sph.data(), b.sph.size() * sizeof(f4));

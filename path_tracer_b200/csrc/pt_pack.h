@@ -26,6 +26,7 @@ struct PackedScene {
   std::vector<SphereGeo> sphere_geo, moving_geo;    // indexed like sphere_aux / moving_aux
   std::vector<unsigned char> sphere_chunk_open, moving_chunk_open;  // 1: chunk is never culled (outsized spheres)
   uint32_t n_objects = 0;
+  uint32_t n_media_groups = 0, n_flat_groups = 0, n_late_sphere_groups = 0;
   std::vector<SphereAux> sphere_aux, moving_aux;
   std::vector<ObjAux> rect_aux, box_aux;
   std::vector<TriAux> tri_aux;

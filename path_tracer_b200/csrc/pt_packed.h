@@ -118,6 +118,10 @@ struct SceneDesc {
   // camera's shutter interval changes (the boxes of moving spheres cover their sweep over it)
   uint32_t off_sphere_box, off_moving_box, n_sphere_chunks, n_moving_chunks;
   float cull_bound[3];        // set s serves origins with max |coordinate| <= cull_bound[s]
+  uint32_t n_media_groups;    // constant_medium objects
+  uint32_t n_late_sphere_groups;  // sphere groups BEHIND a constant_medium (the wavefront kernel then scans sequentially per ray)
+  uint32_t n_flat_groups;     // rect / triangle / box groups
+  const int32_t* object_id;   // original object index -> scan id (the wavefront kernel's winner table)
   const SphereAux* sphere_aux;
   const SphereAux* moving_aux;
   const ObjAux* rect_aux;

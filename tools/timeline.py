@@ -19,8 +19,10 @@ for i in range(3):
     ev0.record()
     ds.render_region(cam, w, h, spp, d, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3, torch.cuda.current_stream().cuda_stream)
     ev1.record(); torch.cuda.synchronize()
-    out = (C.c_ulonglong * 5)()
+    out = (C.c_ulonglong * 10)()
     L.pt_debug_timeline(ds._h, out)
     ms = ev0.elapsed_time(ev1)
     print("args %s: total %.2f ms (%.1f Mpaths/s); main kernel: dry %.2f, done %.2f; CTAs out of regular work %.2f / %.2f ms; handed off %d" % (
         " ".join(sys.argv[1:]), ms, w * h * spp / ms / 1e3, out[0] / 1e6, out[1] / 1e6, out[2] / 1e6, out[3] / 1e6, out[4]))
+    print("    service: %d rounds, %.1f rays per round, %.0f rounds per handed-off pixel (longest stay %d); wait in queue avg %.2f ms, max %.2f ms" % (
+        out[5], out[6] / max(out[5], 1), out[6] / max(out[4], 1), out[9], out[7] / max(out[4], 1) / 1e6, out[8] / 1e6))
