@@ -379,12 +379,13 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   p.pool_cap = 0;
   p.scramble = 1;
   p.n_express = g_n_express;
+  p.express_positions = 0;
   p.order_mode = 0, p.tile_order = nullptr, p.tiles_x = p.tiles_y = 0, p.probe_cost = nullptr, p.n_positions = 0;
   p.heavy.ctrl = scene->heavy_ctrl, p.heavy.ready = scene->heavy_ready, p.heavy.entries = scene->heavy_entries;
   p.heavy.cap = kHeavyCap;
   auto next_queue_head = [&]() {
     const int slot = scene->next_slot;
-    scene->next_slot = (slot + 1) % kCounterSlots;
+    scene->next_slot = (slot + 2) % kCounterSlots;  // a pair: everybody's head and the express CTAs'
     return scene->queue_heads + slot;
   };
   PT_CUDA(cudaMemsetAsync(p.counters + 1, 0xff, 2 * sizeof(unsigned long long), st));
@@ -419,7 +420,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
     probe.pixel_counter = next_queue_head();
     probe.heavy.stamp = ++scene->launch_stamp;
     PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
-    PT_CUDA(cudaMemsetAsync(probe.pixel_counter, 0, sizeof(unsigned long long), st));
+    PT_CUDA(cudaMemsetAsync(probe.pixel_counter, 0, 2 * sizeof(unsigned long long), st));
     cudaError_t pe = launch_render(probe, scene->device, 0, st, nullptr);
     if (pe != cudaSuccess) return cuda_fail(pe, "cost probe launch");
     pe = launch_tile_order(probe_cost, region->w, region->h, tiles_x, tiles_y, tile_order, scratch, st);
@@ -430,7 +431,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   p.pixel_counter = next_queue_head();
   p.heavy.stamp = ++scene->launch_stamp;
   PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
-  PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, 2 * sizeof(unsigned long long), st));
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
   scene->kernel_launches += 1;
@@ -456,6 +457,36 @@ int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* sc
 }
 
 // Debug aid (not part of pt_abi.h): force the launch team size (0 = automatic).
+// Test hook (host only, no GPU needed): the chunk layout and the chunk boxes pack_scene / compute_cull_boxes produce.
+// keys: one per sphere element, static elements first (-1 - order index; INT_MIN = padding); boxes: kCullSets sets of
+// (static chunks, then moving chunks) x {lo[3], hi[3]}.  Returns the number of floats boxes needs (fills up to cap).
+int pt_debug_chunk_layout(const pt_scene* scene, float cam_time0, float cam_time1, int* n_static_elements,
+                          int* n_moving_elements, int* keys, int keys_cap, float* boxes, int boxes_cap, float bounds[3]) {
+  if (!scene) return fail(PT_ERR_INVALID_ARGUMENT, "pt_debug_chunk_layout: null scene");
+  PackedScene ps;
+  std::string err;
+  const int rc = pack_scene(*scene, ps, err);
+  if (rc != PT_OK) return fail(rc, err);
+  CullBoxes cb;
+  compute_cull_boxes(ps, cam_time0, cam_time1, cb);
+  *n_static_elements = (int)ps.sphere_aux.size(), *n_moving_elements = (int)ps.moving_aux.size();
+  int k = 0;
+  for (const auto& a : ps.sphere_aux)
+    if (k < keys_cap) keys[k++] = a.key;
+  for (const auto& a : ps.moving_aux)
+    if (k < keys_cap) keys[k++] = a.key;
+  const size_t ns = ps.sphere_chunk_open.size(), nm = ps.moving_chunk_open.size();
+  int at = 0;
+  for (int set = 0; set < kCullSets; ++set)
+    for (size_t c = 0; c < ns + nm; ++c) {
+      const float* b = c < ns ? cb.sphere.data() + ((size_t)set * ns + c) * 8 : cb.moving.data() + ((size_t)set * nm + (c - ns)) * 8;
+      for (int j = 0; j < 6; ++j, ++at)
+        if (at < boxes_cap) boxes[at] = b[j < 3 ? j : j + 1];
+    }
+  for (int j = 0; j < 3; ++j) bounds[j] = cb.bound[j];
+  return at;
+}
+
 int pt_debug_set_cull(int on) {
   g_cull_enabled = on ? 1 : 0;
   return PT_OK;

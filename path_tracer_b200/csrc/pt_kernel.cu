@@ -235,24 +235,26 @@ PT_DEV bool rect_hit_t(const Ray& r, int axis, float a0, float a1, float b0, flo
 // box.hpp:29-50 over the six sides of box.hpp:20-25 (xy@p1.z, xy@p0.z, xz@p1.y, xz@p0.y, yz@p1.x,
 // yz@p0.x; a later side takes a tie).  Returns the winning side or -1.  One loop body instead of six
 // inlined rectangles keeps the code small.
+PT_DEV bool box_side_hit_t(const Ray& r, V3 p0, V3 p1, int s, float tmin, float tmax, float& t, float& a, float& b) {
+  const int axis = s >> 1;  // PT_AXIS_XY, PT_AXIS_XZ, PT_AXIS_YZ
+  const bool hi = (s & 1) == 0;
+  float a0, a1, b0, b1, k;
+  if (axis == PT_AXIS_XY)
+    a0 = p0.x, a1 = p1.x, b0 = p0.y, b1 = p1.y, k = hi ? p1.z : p0.z;
+  else if (axis == PT_AXIS_XZ)
+    a0 = p0.x, a1 = p1.x, b0 = p0.z, b1 = p1.z, k = hi ? p1.y : p0.y;
+  else
+    a0 = p0.y, a1 = p1.y, b0 = p0.z, b1 = p1.z, k = hi ? p1.x : p0.x;
+  return rect_hit_t(r, axis, a0, a1, b0, b1, k, tmin, tmax, t, a, b);
+}
 PT_DEV int box_hit_t(const Ray& r, V3 p0, V3 p1, float tmin, float tmax, float& t_out, float& a_out,
                      float& b_out) {
   int side = -1;
   float closest = tmax;
 #pragma unroll 1
   for (int s = 0; s < 6; ++s) {
-    const int axis = s >> 1;  // PT_AXIS_XY, PT_AXIS_XZ, PT_AXIS_YZ
-    const bool hi = (s & 1) == 0;
-    float a0, a1, b0, b1, k;
-    if (axis == PT_AXIS_XY)
-      a0 = p0.x, a1 = p1.x, b0 = p0.y, b1 = p1.y, k = hi ? p1.z : p0.z;
-    else if (axis == PT_AXIS_XZ)
-      a0 = p0.x, a1 = p1.x, b0 = p0.z, b1 = p1.z, k = hi ? p1.y : p0.y;
-    else
-      a0 = p0.y, a1 = p1.y, b0 = p0.z, b1 = p1.z, k = hi ? p1.x : p0.x;
     float t, a, b;
-    if (rect_hit_t(r, axis, a0, a1, b0, b1, k, tmin, closest, t, a, b))
-      side = s, closest = t, t_out = t, a_out = a, b_out = b;
+    if (box_side_hit_t(r, p0, p1, s, tmin, closest, t, a, b)) side = s, closest = t, t_out = t, a_out = a, b_out = b;
   }
   return side;
 }
@@ -1248,14 +1250,25 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   unsigned int n_scans = 0;
 
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
+  // The first p.express_positions positions of the queue (the most expensive tiles of the LPT order) belong to the
+  // express CTAs, which trace them in short rounds from the start; everybody else begins behind them.
   auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py) -> bool {
     for (;;) {
       if (W.pixel_dry) return false;
-      const unsigned long long pos = atomicAdd(p.pixel_counter, 1ull);
-      if (pos >= p.n_positions) {
-        W.pixel_dry = 1;
-        if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
-        return false;
+      unsigned long long pos;
+      if (express) {
+        pos = atomicAdd(p.pixel_counter + 1, 1ull);
+        if (pos >= p.express_positions) {
+          W.pixel_dry = 1;
+          return false;
+        }
+      } else {
+        pos = p.express_positions + atomicAdd(p.pixel_counter, 1ull);
+        if (pos >= p.n_positions) {
+          W.pixel_dry = 1;
+          if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+          return false;
+        }
       }
       float* unused;
       if (!queue_pixel(p, pos, px, py, unused)) continue;  // a tile position outside the region
@@ -1361,24 +1374,28 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     int nf = 0, late = n_groups;
     for (int gi = 0; gi < n_groups; ++gi) {
       const Group g = sv.groups[gi];
-      if (g.type == G_MEDIUM || ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && nf + g.count > kMaxFlats)) {
+      if (g.type == G_MEDIUM || ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && nf + 6 * g.count > kMaxFlats)) {
         late = gi;
         break;
       }
-      if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX)
+      if (g.type == G_RECT || g.type == G_TRIANGLE)
         for (int i = 0; i < g.count; ++i) W.flats[nf++] = make_int2(g.type, g.begin + i);
+      if (g.type == G_BOX)  // a box is six independent sides (box.hpp:20-25): the closest side is the box's hit
+        for (int i = 0; i < g.count; ++i)
+          for (int side = 0; side < 6; ++side) W.flats[nf++] = make_int2(G_BOX | (side << 8), g.begin + i);
     }
     W.n_flats = nf, W.first_late_group = late;
   }
   if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
   if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
-  if (!express) {
+  {
     // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
+    const int cap = express ? kExpressPool : p.pool_cap;
     for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
       const int slot = s0 + lane;
       bool alive = false;
-      if (slot < p.pool_cap) {
+      if (slot < cap) {
         uint32_t pixq;
         Rng rng;
         int px, py;
@@ -1386,11 +1403,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           Ray ray;
           camera_ray(cam, px, py, fwidth, fheight, rng, ray);
           store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
-          W.pix[slot] = pixq, W.scans[slot] = 0;
+          W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;  // (an express CTA never hands a pixel off)
           alive = true;
         }
       }
-      append(alive, true, slot);
+      append(alive, !express, slot);
     }
     __syncthreads();
   }
@@ -1567,10 +1584,18 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int2 fo = W.flats[j];
         const int slot = (int)W.list_a[w - j * n];
         const Ray ray = load_ray(slot);
-        Group g {};
-        g.type = fo.x, g.begin = fo.y, g.count = 1;
         Best b { kInf, -1 };
-        scan_flat_group<kSmem>(sc, sv, g, ray, fo.y, 1, b);
+        if ((fo.x & 255) == G_BOX) {
+          const float4 p0 = ld4<kSmem>(sv.box + 2 * fo.y);
+          const float4 p1 = ld4<kSmem>(sv.box + 2 * fo.y + 1);
+          float t, ra, rb;
+          if (box_side_hit_t(ray, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), fo.x >> 8, kTMin, kInf, t, ra, rb))
+            b.t = t, b.id = make_id(G_BOX, fo.y);
+        } else {
+          Group g {};
+          g.type = fo.x, g.begin = fo.y, g.count = 1;
+          scan_flat_group<kSmem>(sc, sv, g, ray, fo.y, 1, b);
+        }
         if (b.id >= 0) atomicMin(&W.best64[slot], pack_winner(b.t, key_of(sc, b.id)));
       }
       __syncthreads();
@@ -1709,8 +1734,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             att = v3(1.f, 1.f, 1.f);
             acc = v3(0.f, 0.f, 0.f);
             bounce = 0, sample = 0;
-            W.pix[slot] = pixq, W.scans[slot] = 0;
-            own = true;
+            W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;
+            own = !express;
           } else if (mode == 1) {
             W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;  // refilled from the hand-off queue
           }
@@ -1807,7 +1832,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
     // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
-    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 9) / 18 : 0);  // 8 of 148: measured best on the default scene
+    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 3) / 6 : 0);  // 25 of 148: measured best on the default scene
     if (q.n_express >= grid) q.n_express = grid - 1;
     if (p.order_mode == 2) {
       q.n_express = 0;
@@ -1817,6 +1842,12 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
       q.n_positions = (unsigned long long)p.tiles_x * (unsigned long long)p.tiles_y * (unsigned long long)(kTile * kTile);
     } else {
       q.n_positions = pixels;
+    }
+    // with the LPT order the express CTAs start on the most expensive tiles, one pixel per pool slot
+    q.express_positions = 0;
+    if (p.order_mode == 1) {
+      q.express_positions = (unsigned long long)q.n_express * (unsigned long long)kExpressPool;
+      if (q.express_positions > q.n_positions) q.express_positions = q.n_positions;
     }
     {
       const unsigned long long sh = (q.n_positions + (unsigned long long)grid - 1ull) / (unsigned long long)grid;

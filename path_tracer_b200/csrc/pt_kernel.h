@@ -38,7 +38,8 @@ struct RenderParams {
   pt_region region;
   float* out;               // device (or peer-mapped) pointer
   long long out_row_pitch;  // floats
-  unsigned long long* pixel_counter;  // work-queue head, zeroed before launch
+  unsigned long long* pixel_counter;  // work-queue heads ([0] everybody's, [1] the express CTAs'), zeroed before launch
+  unsigned long long express_positions;  // leading queue positions reserved for the express CTAs (set by the launcher)
   unsigned long long* counters;       // [0] += closest-hit scans (may be null)
   int team_size;                      // lane kernel: lanes per pixel at launch (power of two, 1..32; 0 = automatic)
   int kernel_kind;                    // 0 = wavefront kernel (default), 1 = lane kernel

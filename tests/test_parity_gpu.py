@@ -275,3 +275,82 @@ def test_single_process_multi_gpu(c1):
     finally:
         R.set_num_gpus(1)
     assert np.array_equal(_bits(one), _bits(two))
+
+
+# ---------------------------------------------------------------- chunk culling (pt_kernel.cu "CHUNK CULLING")
+def _scene_by_name(name):
+    if name == "c1":
+        sc, cam, _ = scenes.load_c1()
+        return sc, cam
+    if name.startswith("random"):
+        return scenes.random_scene(int(name[6:]), n_objects=90, aspect=4 / 3)
+    return getattr(scenes, name)(4 / 3)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("name", ["c1", "rtiow", "motion_blur", "moving", "media", "shapes", "random1", "random5"])
+def test_chunk_culling_is_invisible(name, kernel):
+    """Skipping the chunks whose box a ray misses is an optimisation only: the same bits with and without it, in both
+    kernels (the wavefront kernel's (ray, chunk) items and the lane kernel's per-lane chunk lists)."""
+    sc, cam = _scene_by_name(name)
+    L = R.lib()
+    try:
+        L.pt_debug_set_kernel(kernel)
+        L.pt_debug_set_cull(0)
+        plain = R.render(sc, cam, 120, 90, 6, 50)
+        scans_plain = R.stats()["scans"]
+        L.pt_debug_set_cull(1)
+        culled = R.render(sc, cam, 120, 90, 6, 50)
+        assert np.array_equal(_bits(plain), _bits(culled)), name
+        assert R.stats()["scans"] == scans_plain
+    finally:
+        L.pt_debug_set_cull(1)
+        L.pt_debug_set_kernel(0)
+
+
+@pytest.mark.parametrize("scale", [1.0, 6.0, 40.0, 300.0, 5000.0, 2.0e6])
+def test_far_camera_uses_wider_box_sets(cport, scale):
+    """Origins far from the scene are served by box sets with larger margins, and beyond the last bound by no culling at
+    all (the reference's own discriminant is noise there): parity with the oracle at every distance."""
+    sc, _ = scenes.rtiow(4 / 3, n=6)
+    cam = scenes.make_camera(tuple(np.float32(scale) * np.array([13, 2, 3], np.float32)), (0, 0, 0), (0, 1, 0),
+                             20.0 / scale, 4 / 3, 0.0, 10.0 * scale)
+    got = R.render(sc, cam, 64, 48, 6, 50)
+    st = R.stats()
+    want, cnt = cport.render(sc, cam, 64, 48, 6, 50)
+    assert_parity(got, want, scale)
+    assert st["scans"] == cnt.scans
+
+
+def test_chunk_boxes_follow_the_shutter(cport):
+    """The boxes of moving spheres cover their sweep over the camera's shutter interval; a device scene recomputes them
+    when a render brings another interval (also one that extrapolates the spheres' own time range)."""
+    import torch
+    sc, _ = scenes.motion_blur(4 / 3)
+    ds = R.DeviceScene(sc, 0)
+    w, h = 96, 72
+    fb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
+    try:
+        for t0, t1 in [(0.0, 1.0), (0.25, 0.3), (-1.5, 3.0), (0.0, 1.0), (0.9, 0.1)]:
+            cam = scenes.make_camera((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, w / h, 0.1, 10.0, t0, t1)
+            ds.render_region(cam, w, h, 4, 50, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3,
+                             torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            want, _ = cport.render(sc, cam, w, h, 4, 50)
+            assert_parity(fb.cpu().numpy(), want, (t0, t1))
+    finally:
+        ds.close()
+
+
+def test_degenerate_directions_are_not_culled_wrongly(cport):
+    """Axis-parallel rays (zero direction components: infinite slab reciprocals) through a grid of spheres."""
+    s = scenes.Scene()
+    for i in range(-8, 9):
+        for j in range(-8, 9):
+            s.sphere((float(i), float(j), 0.0), 0.45, s.lambertian((0.5 + 0.02 * i, 0.5, 0.5 + 0.02 * j)))
+    # an orthographic-like camera: tiny field of view from far away, looking straight down the z axis
+    cam = scenes.make_camera((0, 0, 50), (0, 0, 0), (0, 1, 0), 20.0, 1.0, 0.0, 50.0)
+    got = R.render(s, cam, 65, 65, 4, 50)
+    want, cnt = cport.render(s, cam, 65, 65, 4, 50)
+    assert_parity(got, want, "grid")
+    assert R.stats()["scans"] == cnt.scans
