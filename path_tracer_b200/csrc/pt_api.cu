@@ -184,6 +184,7 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
     if (ps.moving_aux[i].material >= 0) object_id[(size_t)(-1 - ps.moving_aux[i].key)] = make_id(G_MOVING_SPHERE, (int)i);
   const size_t o_objid = place(host, object_id);
   const size_t o_mat = place(host, ps.materials);
+  const size_t stage_end = align_up(host.size(), 16);  // what the wavefront kernel keeps in shared memory if it fits
   const size_t o_tex = place(host, ps.textures);
   const size_t o_heads = align_up(host.size(), 256);
   host.resize(o_heads + sizeof(unsigned long long) * (kCounterSlots + kCounterWords), 0);
@@ -230,6 +231,7 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   SceneDesc& d = ds->desc;
   d.blob = ds->arena + o_blob;
   d.blob_bytes = (uint32_t)ps.blob.size();
+  d.stage_bytes = (uint32_t)(stage_end - o_blob);
   d.n_groups = ps.n_groups;
   d.off_groups = ps.off_groups, d.off_sphere = ps.off_sphere, d.off_moving = ps.off_moving;
   d.off_rect = ps.off_rect, d.off_triangle = ps.off_triangle, d.off_box = ps.off_box;

@@ -24,11 +24,16 @@ namespace ptb {
 PT_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
 PT_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
 PT_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
-// IEEE division and square root expand to ~30 / ~15 instructions each; they are never in the scan
-// loop, so ONE out-of-line copy keeps the kernel's instruction footprint small (the scan loop must
-// own the instruction cache, see DESIGN.md "instruction cache").
+// IEEE division and square root, inlined: a few independent ones in a row (a normal's three components, both
+// roots of a sphere) then overlap, which matters in the short rounds that bound the frame's critical path
+// (measured: 1.12 -> 1.21 Gpaths/s on the default scene).  -DPT_OUTLINE_DIV keeps one out-of-line copy instead.
+#ifndef PT_OUTLINE_DIV
+PT_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+PT_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
+#else
 __device__ __noinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __noinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+#endif
 
 struct V3 {
   float x, y, z;

@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 #define PT_EXPRESS_POOL 64
 #endif
 #ifndef PT_WAVE_ITEMS
-#define PT_WAVE_ITEMS 12288
+#define PT_WAVE_ITEMS 4096
 #endif
 constexpr int kWaveThreads = PT_WAVE_THREADS;
 constexpr int kWavePool = PT_WAVE_ROUNDS * kWaveThreads;  // pixels (rays) a CTA keeps in flight: whole scan passes
@@ -1209,22 +1209,39 @@ template <bool kSmem>
 __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wave_kernel(const RenderParams p) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ __align__(8) uint64_t stage_bar;
+  __shared__ SceneDesc staged_scene;  // the scene descriptor with the staged tables' pointers redirected to shared memory
 
-  const SceneDesc& sc = p.scene;
-  const unsigned char* blob_base = sc.blob;
-  const uint32_t pool_offset = kSmem ? ((sc.blob_bytes + 127u) & ~127u) : 0u;
+  const unsigned char* blob_base = p.scene.blob;
+  const uint32_t staged = kSmem ? p.staged_bytes : 0u;  // the scan blob, and the side tables behind it when they fit too
+  const uint32_t pool_offset = (staged + 127u) & ~127u;
   if constexpr (kSmem) {
     if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-      mbar_expect_tx(&stage_bar, sc.blob_bytes);
+      mbar_expect_tx(&stage_bar, staged);
       constexpr uint32_t kPiece = 32768;
-      for (uint32_t off = 0; off < sc.blob_bytes; off += kPiece)
-        bulk_g2s(smem_blob + off, sc.blob + off, min(kPiece, sc.blob_bytes - off), &stage_bar);
+      for (uint32_t off = 0; off < staged; off += kPiece)
+        bulk_g2s(smem_blob + off, p.scene.blob + off, min(kPiece, staged - off), &stage_bar);
     }
-    mbar_wait(&stage_bar, 0);
     blob_base = smem_blob;
   }
+  if (threadIdx.x == 0) {
+    staged_scene = p.scene;
+    const unsigned char* g0 = p.scene.blob;
+    auto redirect = [&](auto& ptr) {
+      const size_t off = (size_t)(reinterpret_cast<const unsigned char*>(ptr) - g0);
+      if (off < (size_t)staged) ptr = reinterpret_cast<decltype(ptr + 0)>(smem_blob + off);
+    };
+    redirect(staged_scene.sphere_aux), redirect(staged_scene.moving_aux), redirect(staged_scene.rect_aux);
+    redirect(staged_scene.tri_aux), redirect(staged_scene.box_aux), redirect(staged_scene.media);
+    redirect(staged_scene.keys), redirect(staged_scene.object_id);
+    const unsigned char* mats = static_cast<const unsigned char*>(staged_scene.materials);
+    redirect(mats);
+    staged_scene.materials = mats;
+  }
+  __syncthreads();
+  if constexpr (kSmem) mbar_wait(&stage_bar, 0);
+  const SceneDesc& sc = staged_scene;
   WavePool& W = *reinterpret_cast<WavePool*>(smem_blob + pool_offset);
   SceneView sv;
   sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
@@ -1512,8 +1529,36 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           const float4* boxes = moving ? sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks
                                        : sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
           const float f = moving ? fdiv(fsub(ray.tm, g.time0), g.den) : 0.f;
-          const int c_first = fine ? blk.y : g.begin / kSphereChunk;
+          // the group's outsized spheres (a ground sphere ...) are tested right here, one by one: their chunks are never
+          // culled and mostly padding (the same sphere for every lane: broadcast loads)
+          const int open_chunks = (g.n_open + kSphereChunk - 1) / kSphereChunk;
+          if (g.n_open > 0 && (!fine || blk.y == g.begin / kSphereChunk)) {
+            const float af = filter_a(a);
+            for (int i = g.begin; i < g.begin + g.n_open; ++i) {
+              float cx, cy, cz, r2f;
+              if (moving) {
+                const float4* ps = sv.moving + moving_slot(i);
+                if ((int)sphere_filter_bits<kSmem, true>(ps, f, ray, af) < 0) {
+                  sphere_center<kSmem, true>(ps, f, cx, cy, cz, r2f);
+                  sphere_roots_scan(sc, inl, ray, a, cx, cy, cz, exact_r2(sc.moving_aux, i), make_id(G_MOVING_SPHERE, i));
+                }
+              } else {
+                const float4* ps = sv.sphere + sphere_slot(i);
+                if ((int)sphere_filter_bits<kSmem, false>(ps, f, ray, af) < 0) {
+                  sphere_center<kSmem, false>(ps, f, cx, cy, cz, r2f);
+                  sphere_roots_scan(sc, inl, ray, a, cx, cy, cz, exact_r2(sc.sphere_aux, i), make_id(G_SPHERE, i));
+                }
+              }
+            }
+          }
+          const int c_group = g.begin / kSphereChunk + open_chunks;  // the first chunk with a box
+          const int c_first = fine ? max(blk.y, c_group) : c_group;
           const int c_end = fine ? blk.y + blk.z : (g.begin + g.count) / kSphereChunk;
+          if (inl.id >= 0) {
+            const unsigned long long w64 = pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, inl);
+            if (w64 < v) v = w64;
+            inl.t = kInf, inl.id = -1;
+          }
           for (int cb = c_first; cb < c_end; cb += 32) {
             emit_items(slot, ray, cr, boxes, moving, cb, min(32, c_end - cb), f, a, inl);
             if (inl.id >= 0) {  // scanned in place: fold into the ray's winner
@@ -1521,6 +1566,19 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
               if (w64 < v) v = w64;
               inl.t = kInf, inl.id = -1;
             }
+          }
+        }
+        if (!fine && W.n_flats != 0) {
+          // many rays: the flat objects in front of the first medium one after the other, here (few rays: one thread per
+          // (ray, object) in SPHERES)
+          Best fb { kInf, -1 };
+          for (int gi = 0; gi < W.first_late_group; ++gi) {
+            const Group g = sv.groups[gi];
+            if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, fb);
+          }
+          if (fb.id >= 0) {
+            const unsigned long long w64 = pack_winner(fb.t, key_of(sc, fb.id));
+            if (w64 < v) v = w64;
           }
         }
         if (v != kNoHit64) atomicMin(&W.best64[slot], v);
@@ -1578,7 +1636,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         }
       }
       // ... and one thread per (ray, flat object) for the rectangles, triangles and boxes in front of the first medium
-      const int n_flats = W.n_flats;
+      const int n_flats = fine ? W.n_flats : 0;
       for (int w = tid; w < n * n_flats; w += kWaveThreads) {
         const int j = w / n;  // object-major: the lanes of a warp test the same object (kind)
         const int2 fo = W.flats[j];
@@ -1814,10 +1872,15 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
   const unsigned long long pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
   if (p.kernel_kind == 0) {
     // ---- wavefront kernel: one CTA per SM, ray pool + (when it fits) the scan blob in shared memory
+    // shared memory: the ray pool, and in front of it the scan blob with the side tables (else the blob alone, else nothing)
     const size_t pool_bytes = sizeof(WavePool);
-    const size_t staged_bytes = ((size_t)p.scene.blob_bytes + 127u) / 128u * 128u + pool_bytes;
-    const bool smem = (long long)staged_bytes <= (long long)max_smem_blob_bytes(device);
-    const size_t dyn = smem ? staged_bytes : pool_bytes;
+    auto with_pool = [&](size_t bytes) { return (bytes + 127u) / 128u * 128u + pool_bytes; };
+    const long long most = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc);
+    q.staged_bytes = (long long)with_pool(p.scene.stage_bytes) <= most  ? p.scene.stage_bytes
+                     : (long long)with_pool(p.scene.blob_bytes) <= most ? p.scene.blob_bytes
+                                                                        : 0u;
+    const bool smem = q.staged_bytes != 0u;
+    const size_t dyn = smem ? with_pool(q.staged_bytes) : pool_bytes;
     auto kernel = smem ? render_wave_kernel<true> : render_wave_kernel<false>;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (err != cudaSuccess) return err;
@@ -1832,7 +1895,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
     // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
-    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 3) / 6 : 0);  // 25 of 148: measured best on the default scene
+    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 3) / 7 : 0);  // 21 of 148: measured best on the default scene
     if (q.n_express >= grid) q.n_express = grid - 1;
     if (p.order_mode == 2) {
       q.n_express = 0;

@@ -44,6 +44,7 @@ struct RenderParams {
   int team_size;                      // lane kernel: lanes per pixel at launch (power of two, 1..32; 0 = automatic)
   int kernel_kind;                    // 0 = wavefront kernel (default), 1 = lane kernel
   int pool_cap;                       // wavefront kernel: pixels a CTA may hold (set by the launcher)
+  unsigned int staged_bytes;          // wavefront kernel: bytes of the arena kept in shared memory (set by the launcher)
   int n_express;                      // wavefront kernel: CTAs that only serve the hand-off queue (< 0 = automatic)
   // pixel order of the wavefront kernel (queue position -> pixel)
   int order_mode;                     // 0 = scrambled, 1 = tiles in `tile_order` (heaviest first), 2 = cost probe grid

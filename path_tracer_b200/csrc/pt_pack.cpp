@@ -92,11 +92,13 @@ struct Builder {
   // Chunk layout of pt_packed.h: outsized spheres first (chunks that are never culled), then the k-d
   // ordered rest; every chunk's entries are written twice in a row.
   static int emit_spheres(std::vector<RawSphere> items, bool moving, std::vector<f4>& data,
-                          std::vector<SphereAux>& aux, std::vector<SphereGeo>& geo, std::vector<unsigned char>& open) {
+                          std::vector<SphereAux>& aux, std::vector<SphereGeo>& geo, std::vector<unsigned char>& open,
+                          int& n_outsized) {
     std::vector<RawSphere> ordered;
     size_t n_open_chunks = 0;
     for (const RawSphere& s : items)
       if (s.outsized) ordered.push_back(s);
+    n_outsized = (int)ordered.size();
     while (ordered.size() % kSphereChunk) ordered.push_back(padding());
     n_open_chunks = ordered.size() / kSphereChunk;
     std::vector<RawSphere> rest;
@@ -122,13 +124,13 @@ struct Builder {
     if (!s.sph.empty()) {
       Group g {};
       g.type = G_SPHERE, g.begin = (int32_t)out.sphere_aux.size();
-      g.count = emit_spheres(s.sph, false, sph, out.sphere_aux, out.sphere_geo, out.sphere_chunk_open);
+      g.count = emit_spheres(s.sph, false, sph, out.sphere_aux, out.sphere_geo, out.sphere_chunk_open, g.n_open);
       groups.push_back(g);
     }
     for (auto& c : s.classes) {
       Group g {};
       g.type = G_MOVING_SPHERE, g.begin = (int32_t)out.moving_aux.size();
-      g.count = emit_spheres(c.items, true, mov, out.moving_aux, out.moving_geo, out.moving_chunk_open);
+      g.count = emit_spheres(c.items, true, mov, out.moving_aux, out.moving_geo, out.moving_chunk_open, g.n_open);
       g.time0 = c.time0, g.den = c.time1 - c.time0;
       groups.push_back(g);
     }

@@ -62,7 +62,8 @@ struct Group {  // 32 bytes
   int32_t count;  // padded count for sphere groups
   float time0;    // G_MOVING_SPHERE: the class's time0
   float den;      // G_MOVING_SPHERE: time1 - time0 (sphere.hpp:55)
-  int32_t pad[3];
+  int32_t n_open; // sphere groups: the first n_open elements are OUTSIZED spheres in chunks of their own that are never culled
+  int32_t pad[2];
 };
 
 // Unified object id carried by the scan: kind in the top bits.
@@ -111,6 +112,7 @@ struct MediumRec {  // constant_medium.hpp:80-82 with its boundary inlined
 struct SceneDesc {
   const unsigned char* blob;  // global copy of the scan blob
   uint32_t blob_bytes;        // multiple of 16
+  uint32_t stage_bytes;       // blob + the side tables that follow it in the arena (aux, media, keys, object ids, materials)
   uint32_t n_groups;
   uint32_t off_groups, off_sphere, off_moving, off_rect, off_triangle, off_box;
   uint32_t n_objects;         // reference n_hittables (for work accounting)
