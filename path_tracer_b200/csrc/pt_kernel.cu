@@ -1074,14 +1074,12 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 //           The work per item is the same whatever the ray, so the lanes of a warp stay busy although
 //           their rays cross different numbers of chunks, and a CTA with few rays left still has
 //           (rays x chunks) items to spread over its threads.
-//   FLAT    one thread per ray: rectangles, triangles, boxes and constant_media in object order against
-//           the running closest hit, then what has to happen next: background, or the kind of the hit
-//           material.
-//   SORT    the rays are counting-sorted by that kind ("compact divergent material work").
-//   SHADE   batches of 32 CONSECUTIVE sorted rays are shaded by one warp each, so the lanes of a warp
-//           run the same material code; finished paths start their pixel's next sample (the RNG
-//           stream of a pixel is strictly serial) or write the pixel and pull a new one from the
-//           global pixel queue.
+//   LATE    one thread per ray: the groups from the first constant_medium on (flat objects and media in object
+//           order against the running closest hit), then what has to happen next -- background, or the kind of
+//           the hit material -- and the ray joins that kind's list ("compact divergent material work").
+//   SHADE   one warp per unit of up to 32 rays of ONE kind, so the lanes of a warp run the same material
+//           code; finished paths start their pixel's next sample (the RNG stream of a pixel is strictly
+//           serial) or write the pixel and pull a new one from the global pixel queue.
 // A scene with spheres BEHIND a constant_medium in the object list is scanned sequentially per ray in
 // BOXES instead (the medium needs the running closest hit of everything before it, and what follows
 // needs the medium's).
@@ -1158,11 +1156,9 @@ struct WavePool {
   int bounce[kWavePool];
   int scans[kWavePool];               // closest-hit scans spent on the current pixel (< 0: taken over, never handed off again)
   unsigned short list_a[kWavePool];   // rays to scan (unordered)
-  unsigned short list_b[kWavePool];   // the same rays sorted by kind
+  unsigned short list_k[kWaveKinds][kWavePool];  // the same rays by kind (what happens next), filled by LATE
   unsigned short free_list[kWavePool];  // hand-off service: pool slots without a pixel
-  unsigned char kind[kWavePool];
   int counts[8];
-  int cursor[8];
   int n_next;      // length of list_a being built
   int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
   int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
@@ -1403,7 +1399,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     }
     W.n_flats = nf, W.first_late_group = late;
   }
-  if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
+  if (tid < 8) W.counts[tid] = 0;
   if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
   {
@@ -1531,8 +1527,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           const float f = moving ? fdiv(fsub(ray.tm, g.time0), g.den) : 0.f;
           // the group's outsized spheres (a ground sphere ...) are tested right here, one by one: their chunks are never
           // culled and mostly padding (the same sphere for every lane: broadcast loads)
-          const int open_chunks = (g.n_open + kSphereChunk - 1) / kSphereChunk;
-          if (g.n_open > 0 && (!fine || blk.y == g.begin / kSphereChunk)) {
+          // (short rounds leave them to SPHERES as items of their never-culled chunks: a shorter chain here)
+          const int open_chunks = fine ? 0 : (g.n_open + kSphereChunk - 1) / kSphereChunk;
+          if (g.n_open > 0 && !fine) {
             const float af = filter_a(a);
             for (int i = g.begin; i < g.begin + g.n_open; ++i) {
               float cx, cy, cz, r2f;
@@ -1661,6 +1658,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     PT_PHASE(1)
 
     // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
+    if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0;  // (SHADE builds the next round's list)
     for (int e = tid; e < n; e += kWaveThreads) {
       const int slot = (int)W.list_a[e];
       Best best;
@@ -1690,47 +1688,32 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       W.scans[slot] += W.scans[slot] >= 0 ? 1 : -1;  // (a taken-over pixel counts downwards: -1 - rounds in the service)
       int kind = 0;
       if (best.id >= 0) kind = 1 + reinterpret_cast<const pt_material*>(sc.materials)[material_of(sc, best.id)].kind;
-      W.kind[slot] = (unsigned char)kind;
-      atomicAdd(&W.counts[kind], 1);
+      W.list_k[kind][atomicAdd(&W.counts[kind], 1)] = (unsigned short)slot;  // "sorted" by kind as a side effect
       ++n_scans;
     }
     __syncthreads();
     PT_PHASE(2)
-
-    // ---- SORT by kind (counting sort; the order inside a kind does not matter)
-    int kind_base[kWaveKinds + 1], unit_base[kWaveKinds + 1];  // rays / 32-ray shading units in front of each kind
-    {
-      int run = 0, units = 0;
-#pragma unroll
-      for (int k = 0; k < kWaveKinds; ++k) {
-        kind_base[k] = run, unit_base[k] = units;
-        run += W.counts[k], units += (W.counts[k] + 31) >> 5;
-      }
-      kind_base[kWaveKinds] = run, unit_base[kWaveKinds] = units;
-      for (int e = tid; e < n; e += kWaveThreads) {
-        const int slot = (int)W.list_a[e];
-        const int k = (int)W.kind[slot];
-        int b = 0;
-#pragma unroll
-        for (int q = 0; q < kWaveKinds; ++q)
-          if (q == k) b = kind_base[q];
-        W.list_b[b + atomicAdd(&W.cursor[k], 1)] = (unsigned short)slot;
-      }
-      if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0;
-    }
-    __syncthreads();
     PT_PHASE(3)
 
-    // ---- SHADE: one warp per unit of up to 32 consecutive sorted rays of ONE kind (no divergence on the material)
-    if (tid < 8) W.counts[tid] = 0, W.cursor[tid] = 0;
+    // ---- SHADE: one warp per unit of up to 32 rays of ONE kind (no divergence on the material)
+    int unit_base[kWaveKinds + 1], kind_count[kWaveKinds];  // 32-ray shading units in front of each kind
+    {
+      int units = 0;
+#pragma unroll
+      for (int k = 0; k < kWaveKinds; ++k) {
+        kind_count[k] = W.counts[k];
+        unit_base[k] = units, units += (kind_count[k] + 31) >> 5;
+      }
+      unit_base[kWaveKinds] = units;
+    }
     const int heavy_rate = W.pixel_dry ? kHeavyRateDry : kHeavyRate;
     for (int u = warp; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
-      int e = 0, e_end = 0;
+      int kind = 0, e = 0, e_end = 0;
 #pragma unroll
       for (int k = 0; k < kWaveKinds; ++k)
-        if (u >= unit_base[k] && u < unit_base[k + 1]) e = kind_base[k] + ((u - unit_base[k]) << 5) + lane, e_end = kind_base[k + 1];
+        if (u >= unit_base[k] && u < unit_base[k + 1]) kind = k, e = ((u - unit_base[k]) << 5) + lane, e_end = kind_count[k];
       const bool act = e < e_end;
-      const int slot = act ? (int)W.list_b[e] : 0;
+      const int slot = act ? (int)W.list_k[kind][e] : 0;
       bool alive = false, own = false;
       if (act) {
         Ray ray = load_ray(slot);
@@ -1803,6 +1786,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       append(alive, own, slot);
     }
     __syncthreads();
+    if (tid < 8) W.counts[tid] = 0;  // (everybody has read them; LATE of the next round is two barriers away)
     PT_PHASE(4)
 #ifdef PT_PHASE_TIMING
     if (tid == 0 && p.counters) atomicAdd(p.counters + 21, 1ull), atomicAdd(p.counters + 22, (unsigned long long)n);

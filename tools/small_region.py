@@ -6,6 +6,8 @@ from path_tracer_b200 import render as R, abi
 # usage: small_region.py x0 y0 w h spp  -> time of a small region (short rounds: the latency of one round)
 x0, y0, rw, rh, spp = (int(a) for a in sys.argv[1:6])
 L = R.lib()
+if len(sys.argv) > 6: L.pt_debug_set_kernel(int(sys.argv[6]))
+if len(sys.argv) > 7: L.pt_debug_set_team_size(int(sys.argv[7]))
 sc, cam, (w, h, _, d) = scenes.load_c1()
 ds = R.DeviceScene(sc, 0)
 fb = torch.zeros((rh, rw, 3), dtype=torch.float32, device="cuda:0")
