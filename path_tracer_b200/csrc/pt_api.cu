@@ -518,8 +518,9 @@ int pt_debug_set_express(int n) {
 
 // Debug aid (not part of pt_abi.h): timeline of the LAST launch on this scene, in ns:
 // out[0] = queue-dry - start, out[1] = last-warp-retired - start.
-// out[5..9]: hand-off service: rounds, ray-rounds, total and longest wait in the queue (ns), longest stay (rounds)
-int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[10]) {
+// out[5..9]: hand-off service: rounds, ray-rounds, total and longest wait in the queue (ns), longest stay (rounds);
+// out[10]: (ray, chunk) items that did not fit the item list and were scanned in place
+int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[11]) {
   PT_CUDA(cudaSetDevice(scene->device));
   PT_CUDA(cudaDeviceSynchronize());
   unsigned long long v[16];
@@ -529,7 +530,7 @@ int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[10]) {
   out[0] = v[2] - v[1], out[1] = v[3] - v[1];
   out[2] = v[5] - v[1], out[3] = v[6] - v[1];  // first / last CTA out of regular work
   out[4] = ctrl[1];                            // heavy pixels handed to the express lane
-  out[5] = v[8], out[6] = v[9], out[7] = v[12], out[8] = v[13], out[9] = v[14];
+  out[5] = v[8], out[6] = v[9], out[7] = v[12], out[8] = v[13], out[9] = v[14], out[10] = v[15];
   if (const char* env = std::getenv("PT_PHASE_TIMING")) {  // debug builds (-DPT_PHASE_TIMING): cycles per phase
     (void)env;
     std::fprintf(stderr, "desc: groups %u media %u flat %u sphere chunks %u moving chunks %u blob %u B\n", scene->desc.n_groups,

@@ -1136,7 +1136,10 @@ constexpr unsigned long long kNoHit64 = 0x7f800000ffffffffull;  // {t = +inf, no
 #define PT_FINE_RAYS 160
 #endif
 constexpr int kFineRays = PT_FINE_RAYS;  // at most this many rays in the round: finer work units (short rounds)
-constexpr int kFineBoxes = 8;            // ... BOXES: a ray's chunks in blocks of this many
+#ifndef PT_FINE_BOXES
+#define PT_FINE_BOXES 8
+#endif
+constexpr int kFineBoxes = PT_FINE_BOXES;            // ... BOXES: a ray's chunks in blocks of this many
 constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in runs of this many
 constexpr int kMaxBoxBlocks = 64;
 constexpr int kMaxFlats = 256;
@@ -1358,10 +1361,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       const int chunk = cb + (nb - 1 - top);
       if (at < (moving ? kWaveItemsMoving : kWaveItemsStatic)) {
         W.items[moving ? kWaveItems - 1 - at : at] = make_uint2((uint32_t)slot | ((uint32_t)chunk << 10), __float_as_uint(f));
-      } else if (moving) {
-        scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
       } else {
-        scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
+        if (p.counters) atomicAdd(p.counters + 15, 1ull);  // stats: items scanned in place (tests check that it happens)
+        if (moving)
+          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
+        else
+          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
       }
       ++at;
     }

@@ -354,3 +354,79 @@ def test_degenerate_directions_are_not_culled_wrongly(cport):
     want, cnt = cport.render(s, cam, 65, 65, 4, 50)
     assert_parity(got, want, "grid")
     assert R.stats()["scans"] == cnt.scans
+
+
+def test_item_list_overflow_is_scanned_in_place(cport):
+    """A grazing camera makes every ray cross many chunk boxes, so a full CTA's (ray, chunk) items do not fit the item
+    list; what does not fit is scanned where it was found.  Large enough that every CTA holds a full pool."""
+    import ctypes as C
+    import torch
+    rs = np.random.RandomState(5)
+    sc = scenes.Scene()
+    mats = [sc.lambertian((0.7, 0.3, 0.3)), sc.metal((0.8, 0.8, 0.8), 0.1), sc.dielectric(1.5), sc.lightsource((2, 2, 2))]
+    for k in range(48):  # 48 clusters of 16 small spheres in a row along z: a ray down the row crosses every cluster's box
+        for i in range(16):
+            c = np.array([rs.uniform(-1.5, 1.5), rs.uniform(-1.5, 1.5), 2.0 * k + rs.uniform(0, 1)], dtype=np.float32)
+            if i % 4 == 0:
+                sc.sphere(c, 0.08, mats[i % 3], center1=c + np.array([0.1, 0, 0], np.float32), time0=0.0, time1=1.0)
+            else:
+                sc.sphere(c, 0.08, mats[(i + k) % 4])
+    cam = scenes.make_camera((0, 0, -12), (0, 0, 50), (0, 1, 0), 1.4, 16 / 9, 0.0, 10.0, 0.0, 1.0)
+    w, h = 640, 360
+    ds = R.DeviceScene(sc, 0)
+    fb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
+    try:
+        ds.render_region(cam, w, h, 2, 50, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        out = (C.c_ulonglong * 11)()
+        R.lib().pt_debug_timeline(ds._h, out)
+        assert out[10] > 1000, "the item list never overflowed: the test does not test what it says"
+        paths, scans = ds.counters()
+    finally:
+        ds.close()
+    got = fb.cpu().numpy()
+    # the lane kernel has no item list: same bits, same scan count
+    L = R.lib()
+    try:
+        L.pt_debug_set_kernel(1)
+        lane = R.render(sc, cam, w, h, 2, 50)
+        assert np.array_equal(_bits(got), _bits(lane)) and R.stats()["scans"] == scans
+    finally:
+        L.pt_debug_set_kernel(0)
+    want, cnt = cport.render(sc, cam, w, h, 2, 50)
+    assert_parity(got, want, "row of clusters")
+    assert abs(scans - cnt.scans) <= 1e-4 * cnt.scans  # (thousands of grazing hits on tiny spheres: a last-bit difference
+    #                                                      in sin / cos now and then changes where a path ends)
+
+
+def test_more_flat_objects_than_the_unit_table_holds(cport):
+    """Flat objects beyond the (ray, object) unit table are scanned sequentially per ray."""
+    sc, cam = scenes.triangle_mesh(4 / 3, nx=24, nz=10)
+    assert len(sc.triangles) > 256
+    got = R.render(sc, cam, 96, 72, 4, 50)
+    st = R.stats()
+    want, cnt = cport.render(sc, cam, 96, 72, 4, 50)
+    assert_parity(got, want, "mesh")
+    assert st["scans"] == cnt.scans
+
+
+def test_scene_too_large_for_shared_memory(cport):
+    """9 000 spheres: the scan blob streams from L2 instead of shared memory, and there are more chunk-box blocks than
+    the short rounds' table holds (they fall back to one thread per ray)."""
+    rs = np.random.RandomState(11)
+    s = scenes.Scene()
+    s.sphere((0, -1000, 0), 1000, s.lambertian((0.5, 0.5, 0.5)))
+    mats = [s.lambertian((0.7, 0.3, 0.3)), s.metal((0.8, 0.8, 0.8), 0.1), s.dielectric(1.5), s.lambertian((0.2, 0.4, 0.8))]
+    for i in range(9000):
+        c = np.array([rs.uniform(-20, 20), rs.uniform(0.1, 3.0), rs.uniform(-20, 20)], dtype=np.float32)
+        if i % 5 == 0:
+            s.sphere(c, 0.1, mats[i % 4], center1=c + np.array([0, 0.2, 0], np.float32), time0=0.0, time1=1.0)
+        else:
+            s.sphere(c, 0.1, mats[i % 4])
+    cam = scenes.make_camera((30, 6, 8), (0, 1, 0), (0, 1, 0), 30.0, 4 / 3, 0.0, 10.0, 0.0, 1.0)
+    for w, h, spp in ((64, 48, 3), (400, 300, 1)):
+        got = R.render(s, cam, w, h, spp, 50)
+        st = R.stats()
+        want, cnt = cport.render(s, cam, w, h, spp, 50)
+        assert_parity(got, want, ("large", w, h))
+        assert st["scans"] == cnt.scans

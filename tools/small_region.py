@@ -17,7 +17,7 @@ for i in range(3):
     ev0.record()
     ds.render_region(cam, w, h, spp, d, abi.pt_region(x0, y0, rw, rh, 1), fb.data_ptr(), rw * 3, torch.cuda.current_stream().cuda_stream)
     ev1.record(); torch.cuda.synchronize()
-    out = (C.c_ulonglong * 10)()
+    out = (C.c_ulonglong * 11)()
     L.pt_debug_timeline(ds._h, out)
     ms = ev0.elapsed_time(ev1)
     paths, scans = ds.counters(reset=True)

@@ -19,7 +19,7 @@ for i in range(3):
     ev0.record()
     ds.render_region(cam, w, h, spp, d, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3, torch.cuda.current_stream().cuda_stream)
     ev1.record(); torch.cuda.synchronize()
-    out = (C.c_ulonglong * 10)()
+    out = (C.c_ulonglong * 11)()
     L.pt_debug_timeline(ds._h, out)
     ms = ev0.elapsed_time(ev1)
     print("args %s: total %.2f ms (%.1f Mpaths/s); main kernel: dry %.2f, done %.2f; CTAs out of regular work %.2f / %.2f ms; handed off %d" % (
