@@ -1432,11 +1432,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 
   for (unsigned int round = 0;; ++round) {
     if (mode == 1) {
-      // ---- hand-off service: fill the free pool slots from the global queue (polled every 4th round:
-      // a poll is a round trip to L2)
+      // ---- hand-off service: fill the free pool slots from the global queue (polled every 8th round: a poll is
+      // two round trips to L2, and these rounds are the frame's critical path)
       const int room = W.free_count, waiting = W.n_next;
-      __syncthreads();  // everybody has read the two before anybody changes them
-      if (room > 0 && ((round & 3u) == 0u || waiting == 0)) {
+      if (room > 0 && ((round & 7u) == 0u || waiting == 0)) {
+        __syncthreads();  // everybody has read the two (and decided alike) before anybody changes them
         int got = -1;
         if (tid < room) got = take_heavy();
         if (got >= 0) {
