@@ -1,32 +1,32 @@
 // pt_kernel.cu -- the per-pixel path-tracing loop of triSYCL/path_tracer
-// (reference include/render.hpp:25-106 and everything it calls) as ONE
-// persistent sm_100a kernel.
+// (reference include/render.hpp:25-106 and everything it calls) as persistent sm_100a kernels.
 //
 // Execution model (B200-first, not a translation of the SYCL kernel):
-//   * Persistent CTAs.  A pixel's `spp` samples are inherently serial -- its xorshift32 stream is
-//     consumed in a data-dependent way (render.hpp:95-101) -- so the unit of work is a PIXEL, pulled
-//     from a global atomic queue; a finished pixel is replaced at once ("path regeneration") and
-//     the warp re-converges at the closest-hit scan with live rays.
-//   * A warp holds k pixels, k = 32 / T, each owned by a TEAM of T lanes that carry the pixel's
-//     path state REPLICATED (same inputs, same instructions => same values, no communication).
-//     T = 1 in steady state.  The scan (render.hpp:30-51) is split inside a team: member m tests
-//     objects m, m+T, ...; the members' winners are merged with shuffles under the rule
-//     (minimum t, then maximum key) that reproduces the sequential scan's tie behaviour exactly
-//     (pt_packed.h), so the result is bit-identical for every T.  When the queue has run dry and
-//     at most half of a warp's teams still own a pixel, the survivors are RE-PACKED into teams
-//     twice as large: the image's deepest pixels (paths bouncing dozens of times inside glass hold
-//     ten times the average work) are traced with ever shorter rounds instead of sitting on a
-//     serial critical path, and a GPU with few pixels per lane (multi-GPU strong scaling) starts
-//     with T > 1.
-//   * The scene's scan blob (pt_packed.h) is staged into shared memory with cp.async.bulk (TMA)
-//     once per CTA and streamed with broadcast LDS.128.  Sphere tests are two-phase: a branch-free
-//     discriminant pass that only records a per-lane candidate bitmask, and an exact root pass
-//     (sqrt, IEEE division, range and tie rules) over the few set bits.  Only `t` and the object
-//     id are tracked; the full hit_record is rebuilt once, for the winner.
-//   * Shading (material scatter / emission / textures) is divergent by nature; it is short
-//     compared with the scan.  Everything outside the scan loops is kept small (out-of-line
-//     division, square root and trigonometry; table-driven box) because the loops must own the
-//     instruction cache.
+//   * A pixel's `spp` samples are inherently serial -- its xorshift32 stream is consumed in a
+//     data-dependent way (render.hpp:95-101) -- so the unit of work is a PIXEL, pulled from a global
+//     atomic queue; a finished pixel is replaced at once ("path regeneration").  Parallelism is
+//     pixels x objects.
+//   * The scene's scan blob (pt_packed.h) and its side tables are staged into shared memory with
+//     cp.async.bulk (TMA) once per CTA.  Spheres come in k-d ordered CHUNKS of 16 behind conservative
+//     bounding boxes; a ray only looks at the chunks whose box it crosses ("chunk culling" below: a proof,
+//     the result is bit-identical with and without it).  Sphere tests are two-phase: a branch-free FMA
+//     filter that only records a candidate bitmask, and the exact roots (sqrt, IEEE division, range and
+//     tie rules) over the few set bits.  Only `t` and the object id are tracked; the hit_record is
+//     rebuilt once, for the winner.
+//   * The winner of a scan is (minimum t, then maximum key), which reproduces the sequential scan's tie
+//     behaviour for ANY visiting order (pt_packed.h): that is what allows skipping chunks, splitting a
+//     scan over lanes or work items, and merging with shuffles or one 64-bit atomicMin.
+//   * render_wave_kernel (default): one 896-thread CTA per SM, the path state of 896 pixels in a
+//     structure-of-arrays pool in shared memory, phases BOXES / SPHERES / LATE / SHADE separated by
+//     __syncthreads(); the closest-hit scan runs as (ray, chunk) work items spread over the whole CTA;
+//     shading runs in warps of one material kind.  Deep pixels (paths bouncing dozens of times inside
+//     glass hold ten times the average work and would sit on a serial critical path) are traced by
+//     EXPRESS CTAs in short rounds, from the head of a longest-processing-time-first pixel order and
+//     from a global hand-off queue.
+//   * render_kernel (lane kernel): a warp holds k = 32 / T pixels, each owned by a TEAM of T lanes that
+//     carry the pixel's path state REPLICATED; the scan is split inside a team and merged with shuffles,
+//     bit-identical for every T.  The simpler scheduler, and the scan of the wavefront kernel's
+//     sequential fallback.
 // All arithmetic follows the operation order of the reference; see pt_device.cuh for the
 // numerics contract.
 #include <cuda_runtime.h>
