@@ -1270,18 +1270,18 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   // express CTAs, which trace them in short rounds from the start; everybody else begins behind them.
   auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py) -> bool {
     for (;;) {
-      if (W.pixel_dry) return false;
+      if (*reinterpret_cast<volatile int*>(&W.pixel_dry)) return false;  // (a set-once flag; a stale 0 only costs one more atomic)
       unsigned long long pos;
       if (express) {
         pos = atomicAdd(p.pixel_counter + 1, 1ull);
         if (pos >= p.express_positions) {
-          W.pixel_dry = 1;
+          atomicExch(&W.pixel_dry, 1);
           return false;
         }
       } else {
         pos = p.express_positions + atomicAdd(p.pixel_counter, 1ull);
         if (pos >= p.n_positions) {
-          W.pixel_dry = 1;
+          atomicExch(&W.pixel_dry, 1);
           if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
           return false;
         }
@@ -1711,7 +1711,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
       unit_base[kWaveKinds] = units;
     }
-    const int heavy_rate = W.pixel_dry ? kHeavyRateDry : kHeavyRate;
+    const int heavy_rate = *reinterpret_cast<volatile int*>(&W.pixel_dry) ? kHeavyRateDry : kHeavyRate;
     for (int u = warp; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
       int kind = 0, e = 0, e_end = 0;
 #pragma unroll
