@@ -837,15 +837,11 @@ PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, 
 
 // ---------------------------------------------------------------- the lane loop
 // One warp, k = 32 / team_size pixels at a time, the path state of each pixel replicated in the
-// registers of its team (see the header comment).  kExpress = false: pixels come from the pixel queue
-// (the lane kernel).  kExpress = true: complete path states come from the hand-off queue of the
-// wavefront kernel and are traced to their last sample (the express service).
-template <bool kSmem, bool kExpress>
+// registers of its team (see the header comment); pixels come from the pixel queue.
+template <bool kSmem>
 PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneView& sv, int team_size0,
                       unsigned int& n_scans) {
-  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
   const pt_camera& cam = p.cam;
-  const unsigned long long n_pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
   const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
 
   // per-lane path state, replicated across the lanes of a team
@@ -906,77 +902,26 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
     {
       const bool wants = need_path && !live && !exhausted_queue;
       if (__any_sync(0xffffffffu, wants)) {
-        if constexpr (!kExpress) {
-          unsigned long long idx = 0ull;
-          if (wants && member == 0) {  // the team leader pulls the next pixel (skipping tile positions outside the region)
-            int tx, ty;
-            float* tp;
-            do idx = atomicAdd(p.pixel_counter, 1ull);
-            while (idx < p.n_positions && !queue_pixel(p, idx, tx, ty, tp));
-          }
-          idx = __shfl_sync(0xffffffffu, idx, lane - member);
-          if (wants) {
-            if (idx < p.n_positions) {
-              queue_pixel(p, idx, px, py, out_px);
-              // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
-              rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
-              acc = v3(0.f, 0.f, 0.f);
-              sample = 0;
-              pix_scans = 0;
-              live = true;
-            } else {
-              exhausted_queue = true;
-              if (p.counters && member == 0) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
-            }
-          }
-        } else {
-          // express service: the team leader takes a handed-off pixel (complete path state) from the global queue
-          const HeavyQueue& hq = p.heavy;
-          int j = -1;  // -1: nothing now, -2: never again
-          if (wants && member == 0) {
-            unsigned int h = ld_volatile_u32(hq.ctrl + 0);
-            for (int attempt = 0; attempt < 8; ++attempt) {
-              const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
-              if (h >= t) {
-                if (ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
-                    ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap))
-                  j = -2;  // every producer is done and the queue is empty
-                break;
-              }
-              const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
-              if (seen == h) {
-                j = (int)h;
-                break;
-              }
-              h = seen;
-            }
-            if (j >= 0) {
-              while (ld_volatile_u32(hq.ready + j) != hq.stamp && globaltimer_ns() <= t_give_up) __nanosleep(100);
-              __threadfence();
-            }
-            if (globaltimer_ns() > t_give_up) {
-              if (p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
-              j = -2;
-            }
-          }
-          j = __shfl_sync(0xffffffffu, j, lane - member);
-          if (wants) {
-            if (j >= 0) {
-              const float* e = hq.entries + (size_t)j * kHeavyEntryWords;
-              queue_pixel(p, (unsigned long long)__float_as_uint(__ldcg(e + 0)), px, py, out_px);
-              rng.s = __float_as_uint(__ldcg(e + 1));
-              sample = __float_as_int(__ldcg(e + 2)), bounce = __float_as_int(__ldcg(e + 3));
-              ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
-              ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
-              ray.tm = __ldcg(e + 10);
-              att = v3(__ldcg(e + 11), __ldcg(e + 12), __ldcg(e + 13));
-              acc = v3(__ldcg(e + 14), __ldcg(e + 15), __ldcg(e + 16));
-              pix_scans = 0;
-              live = true;
-              need_path = false;  // the pixel continues in the middle of a path
-            } else if (j == -2) {
-              exhausted_queue = true;
-            }
+        unsigned long long idx = 0ull;
+        if (wants && member == 0) {  // the team leader pulls the next pixel (skipping tile positions outside the region)
+          int tx, ty;
+          float* tp;
+          do idx = atomicAdd(p.pixel_counter, 1ull);
+          while (idx < p.n_positions && !queue_pixel(p, idx, tx, ty, tp));
+        }
+        idx = __shfl_sync(0xffffffffu, idx, lane - member);
+        if (wants) {
+          if (idx < p.n_positions) {
+            queue_pixel(p, idx, px, py, out_px);
+            // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+            rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+            acc = v3(0.f, 0.f, 0.f);
+            sample = 0;
+            pix_scans = 0;
+            live = true;
+          } else {
+            exhausted_queue = true;
+            if (p.counters && member == 0) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
           }
         }
       }
@@ -989,7 +934,6 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
     }
     if (!__any_sync(0xffffffffu, live)) {
       if (__all_sync(0xffffffffu, exhausted_queue)) break;
-      __nanosleep(300);  // express service: wait for hand-offs
       continue;
     }
 
@@ -1010,7 +954,7 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
     // A warp that finds itself holding one of the image's deepest pixels stops taking new pixels: as its
     // other pixels finish it is re-packed into ever larger teams, until all 32 lanes scan for the deep
     // pixel and its remaining thousands of bounces take microseconds each instead of a full round.
-    if (!kExpress && __any_sync(0xffffffffu, live && pix_scans > kDeepBase + kDeepRate * sample)) exhausted_queue = true;
+    if (__any_sync(0xffffffffu, live && pix_scans > kDeepBase + kDeepRate * sample)) exhausted_queue = true;
   }
 
 }
@@ -1051,7 +995,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   unsigned int n_scans = 0;
-  lane_loop<kSmem, false>(p, sc, sv, p.team_size, n_scans);
+  lane_loop<kSmem>(p, sc, sv, p.team_size, n_scans);
 
   if (p.counters && (threadIdx.x & 31) == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   // work counters: one atomic per warp
@@ -1111,9 +1055,6 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 #ifndef PT_HEAVY_RATE_DRY
 #define PT_HEAVY_RATE_DRY 10
 #endif
-#ifndef PT_EXPRESS_TEAM
-#define PT_EXPRESS_TEAM 16
-#endif
 #ifndef PT_EXPRESS_POOL
 #define PT_EXPRESS_POOL 64
 #endif
@@ -1126,7 +1067,6 @@ constexpr int kWaveKinds = 6;                              // 0 = background, 1 
 constexpr int kHeavyRate = PT_HEAVY_RATE;                  // heavy: more than kHeavyBase + rate * samples scans so far
 constexpr int kHeavyRateDry = PT_HEAVY_RATE_DRY;           // ... a lower bar once the pixel queue is dry (load sharing)
 constexpr int kHeavyBase = 64;
-constexpr int kExpressTeam = PT_EXPRESS_TEAM;              // lane kernel's express service (unused by the wavefront kernel)
 constexpr int kExpressPool = PT_EXPRESS_POOL;              // rays in flight in a CTA that serves the hand-off queue
 constexpr int kWaveItems = PT_WAVE_ITEMS;                  // (ray, chunk) items per round; the overflow is scanned in place
 constexpr int kWaveItemsStatic = kWaveItems * 3 / 8;       // ... of static spheres (from the front of the list)
@@ -1229,7 +1169,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     const unsigned char* g0 = p.scene.blob;
     auto redirect = [&](auto& ptr) {
       const size_t off = (size_t)(reinterpret_cast<const unsigned char*>(ptr) - g0);
-      if (off < (size_t)staged) ptr = reinterpret_cast<decltype(ptr + 0)>(smem_blob + off);
+      if (kSmem && off < (size_t)staged) ptr = reinterpret_cast<decltype(ptr + 0)>(smem_blob + off);
     };
     redirect(staged_scene.sphere_aux), redirect(staged_scene.moving_aux), redirect(staged_scene.rect_aux);
     redirect(staged_scene.tri_aux), redirect(staged_scene.box_aux), redirect(staged_scene.media);

@@ -20,8 +20,8 @@ constexpr int kMinBlocksPerSM = PT_MIN_BLOCKS_PER_SM;
 constexpr int kMaxBlocksPerSM = PT_MIN_BLOCKS_PER_SM;  // persistent grid = SMs x this
 
 // Global hand-off queue for HEAVY pixels (wavefront kernel): bounded, written once per entry per
-// launch, consumed by the express warps of every CTA.  ctrl[0] = head, ctrl[1] = tail, ctrl[2] = CTAs
-// whose regular work is finished.
+// launch, consumed by the express CTAs and by every CTA whose own pixels have run out.  ctrl[0] = head,
+// ctrl[1] = tail, ctrl[2] = CTAs whose regular work is finished (they hand nothing off any more).
 constexpr int kHeavyEntryWords = 20;
 struct HeavyQueue {
   unsigned int* ctrl;
