@@ -430,3 +430,23 @@ def test_scene_too_large_for_shared_memory(cport):
         want, cnt = cport.render(s, cam, w, h, spp, 50)
         assert_parity(got, want, ("large", w, h))
         assert st["scans"] == cnt.scans
+
+
+def test_negative_radius_and_nested_spheres(cport):
+    """RTIOW's hollow glass bubble (a sphere of negative radius inside a glass sphere: same geometry, flipped normal,
+    sphere.hpp:81) and concentric shells around it -- chunk boxes are built from |radius|."""
+    s = scenes.Scene()
+    s.sphere((0, -100.5, -1), 100, s.lambertian((0.8, 0.8, 0.0)))
+    s.sphere((0, 0, -1), 0.5, s.dielectric(1.5))
+    s.sphere((0, 0, -1), -0.45, s.dielectric(1.5))
+    s.sphere((0, 0, -1), 0.2, s.lambertian((0.1, 0.2, 0.5)))
+    s.sphere((-1, 0, -1), 0.5, s.metal((0.8, 0.6, 0.2), 0.0))
+    s.sphere((1, 0, -1), -0.5, s.metal((0.8, 0.8, 0.8), 0.3))
+    for i in range(40):
+        s.sphere((-2 + 0.1 * i, -0.4, -0.3 - 0.02 * i), 0.05 if i % 2 else -0.05, s.lambertian((0.5, 0.1 + 0.02 * i, 0.3)))
+    cam = scenes.make_camera((-2, 2, 1), (0, 0, -1), (0, 1, 0), 35.0, 4 / 3, 0.0, 3.4)
+    got = R.render(s, cam, 160, 120, 8, 50)
+    st = R.stats()
+    want, cnt = cport.render(s, cam, 160, 120, 8, 50)
+    assert_parity(got, want, "hollow glass")
+    assert st["scans"] == cnt.scans
