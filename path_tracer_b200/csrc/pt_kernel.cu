@@ -1536,67 +1536,70 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       if (tid == 0 && p.counters) atomicAdd(p.counters + 23, (unsigned long long)(n_s + n_m));
 #endif
       if (!fine) {
-        for (int i = tid; i < n_s; i += kWaveThreads) {
-          const uint2 it = W.items[i];
-          const int slot = (int)(it.x & 1023u);
-          const Ray ray = load_ray(slot);
-          const float a = vdot(ray.d, ray.d);
-          Best b { kInf, -1 };
-          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
-                                                    G_SPHERE, b);
-          if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(sc.sphere_aux, b));
-        }
-        for (int i = tid; i < n_m; i += kWaveThreads) {
-          const uint2 it = W.items[kWaveItems - 1 - i];
-          const int slot = (int)(it.x & 1023u);
-          const Ray ray = load_ray(slot);
-          const float a = vdot(ray.d, ray.d);
-          Best b { kInf, -1 };
-          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
-                                                   __uint_as_float(it.y), G_MOVING_SPHERE, b);
-          if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(sc.moving_aux, b));
-        }
-      } else {
-        // the kParts threads of an item are neighbouring lanes: lane & 15 = 4 m + q takes slots 4 m + q + 4 k (like a team of 4)
-        constexpr int kParts = kSphereChunk / kFineQuarter;
-        static_assert(kWaveThreads % kParts == 0 && kParts == 4, "an item's threads must be lanes 4 m .. 4 m + 3");
-        for (int w = tid; w < kParts * (n_s + n_m); w += kWaveThreads) {
-          const int i = w / kParts;
-          const bool moving = i >= n_s;
-          const uint2 it = W.items[moving ? kWaveItems - 1 - (i - n_s) : i];
+        // one index space for both kinds (a thread's items follow each other without a pass boundary in between); the
+        // moving items start at a warp boundary so that a warp runs one kind's code
+        const int m_base = (n_s + 31) & ~31;
+        for (int i = tid; i < m_base + n_m; i += kWaveThreads) {
+          if (i >= n_s && i < m_base) continue;
+          const bool moving = i >= m_base;
+          const uint2 it = W.items[moving ? kWaveItems - 1 - (i - m_base) : i];
           const int slot = (int)(it.x & 1023u);
           const Ray ray = load_ray(slot);
           const float a = vdot(ray.d, ray.d);
           Best b { kInf, -1 };
           if (moving)
-            scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
-                                                          __uint_as_float(it.y), G_MOVING_SPHERE, b);
+            scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                     __uint_as_float(it.y), G_MOVING_SPHERE, b);
           else
-            scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
-                                                           0.f, G_SPHERE, b);
+            scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
+                                                      G_SPHERE, b);
           if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
         }
-      }
-      // ... and one thread per (ray, flat object) for the rectangles, triangles and boxes in front of the first medium
-      const int n_flats = fine ? W.n_flats : 0;
-      for (int w = tid; w < n * n_flats; w += kWaveThreads) {
-        const int j = w / n;  // object-major: the lanes of a warp test the same object (kind)
-        const int2 fo = W.flats[j];
-        const int slot = (int)W.list_a[w - j * n];
-        const Ray ray = load_ray(slot);
-        Best b { kInf, -1 };
-        if ((fo.x & 255) == G_BOX) {
-          const float4 p0 = ld4<kSmem>(sv.box + 2 * fo.y);
-          const float4 p1 = ld4<kSmem>(sv.box + 2 * fo.y + 1);
-          float t, ra, rb;
-          if (box_side_hit_t(ray, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), fo.x >> 8, kTMin, kInf, t, ra, rb))
-            b.t = t, b.id = make_id(G_BOX, fo.y);
-        } else {
-          Group g {};
-          g.type = fo.x, g.begin = fo.y, g.count = 1;
-          scan_flat_group<kSmem>(sc, sv, g, ray, fo.y, 1, b);
+      } else {
+        // Short rounds, ONE unit per thread where possible: a quarter of an item (its kParts threads are neighbouring lanes:
+        // lane & 15 = 4 m + q takes slots 4 m + q + 4 k, like a team of 4), or one (ray, flat object) pair for the
+        // rectangles, triangles and box sides in front of the first medium (object-major: a warp tests one object).
+        constexpr int kParts = kSphereChunk / kFineQuarter;
+        static_assert(kWaveThreads % kParts == 0 && kParts == 4, "an item's threads must be lanes 4 m .. 4 m + 3");
+        const int n_quarters = kParts * (n_s + n_m);
+        const int f_base = (n_quarters + 31) & ~31;
+        const int n_flats = W.n_flats;
+        for (int w = tid; w < f_base + n * n_flats; w += kWaveThreads) {
+          if (w < n_quarters) {
+            const int i = w / kParts;
+            const bool moving = i >= n_s;
+            const uint2 it = W.items[moving ? kWaveItems - 1 - (i - n_s) : i];
+            const int slot = (int)(it.x & 1023u);
+            const Ray ray = load_ray(slot);
+            const float a = vdot(ray.d, ray.d);
+            Best b { kInf, -1 };
+            if (moving)
+              scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                            __uint_as_float(it.y), G_MOVING_SPHERE, b);
+            else
+              scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                             0.f, G_SPHERE, b);
+            if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
+          } else if (w >= f_base) {
+            const int j = (w - f_base) / n;
+            const int2 fo = W.flats[j];
+            const int slot = (int)W.list_a[(w - f_base) - j * n];
+            const Ray ray = load_ray(slot);
+            Best b { kInf, -1 };
+            if ((fo.x & 255) == G_BOX) {
+              const float4 p0 = ld4<kSmem>(sv.box + 2 * fo.y);
+              const float4 p1 = ld4<kSmem>(sv.box + 2 * fo.y + 1);
+              float t, ra, rb;
+              if (box_side_hit_t(ray, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), fo.x >> 8, kTMin, kInf, t, ra, rb))
+                b.t = t, b.id = make_id(G_BOX, fo.y);
+            } else {
+              Group g {};
+              g.type = fo.x, g.begin = fo.y, g.count = 1;
+              scan_flat_group<kSmem>(sc, sv, g, ray, fo.y, 1, b);
+            }
+            if (b.id >= 0) atomicMin(&W.best64[slot], pack_winner(b.t, key_of(sc, b.id)));
+          }
         }
-        if (b.id >= 0) atomicMin(&W.best64[slot], pack_winner(b.t, key_of(sc, b.id)));
       }
       __syncthreads();
     }
