@@ -1150,9 +1150,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   __shared__ __align__(8) uint64_t stage_bar;
   __shared__ SceneDesc staged_scene;  // the scene descriptor with the staged tables' pointers redirected to shared memory
 
+  // dynamic shared memory: the ray pool first (at a compile-time offset, so that its accesses need no address arithmetic),
+  // then the staged part of the arena
+  constexpr uint32_t kPoolBytes = ((uint32_t)sizeof(WavePool) + 127u) & ~127u;
+  unsigned char* const smem_stage = smem_blob + kPoolBytes;
   const unsigned char* blob_base = p.scene.blob;
   const uint32_t staged = kSmem ? p.staged_bytes : 0u;  // the scan blob, and the side tables behind it when they fit too
-  const uint32_t pool_offset = (staged + 127u) & ~127u;
   if constexpr (kSmem) {
     if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
     __syncthreads();
@@ -1160,16 +1163,16 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       mbar_expect_tx(&stage_bar, staged);
       constexpr uint32_t kPiece = 32768;
       for (uint32_t off = 0; off < staged; off += kPiece)
-        bulk_g2s(smem_blob + off, p.scene.blob + off, min(kPiece, staged - off), &stage_bar);
+        bulk_g2s(smem_stage + off, p.scene.blob + off, min(kPiece, staged - off), &stage_bar);
     }
-    blob_base = smem_blob;
+    blob_base = smem_stage;
   }
   if (threadIdx.x == 0) {
     staged_scene = p.scene;
     const unsigned char* g0 = p.scene.blob;
     auto redirect = [&](auto& ptr) {
       const size_t off = (size_t)(reinterpret_cast<const unsigned char*>(ptr) - g0);
-      if (kSmem && off < (size_t)staged) ptr = reinterpret_cast<decltype(ptr + 0)>(smem_blob + off);
+      if (kSmem && off < (size_t)staged) ptr = reinterpret_cast<decltype(ptr + 0)>(smem_stage + off);
     };
     redirect(staged_scene.sphere_aux), redirect(staged_scene.moving_aux), redirect(staged_scene.rect_aux);
     redirect(staged_scene.tri_aux), redirect(staged_scene.box_aux), redirect(staged_scene.media);
@@ -1181,7 +1184,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   __syncthreads();
   if constexpr (kSmem) mbar_wait(&stage_bar, 0);
   const SceneDesc& sc = staged_scene;
-  WavePool& W = *reinterpret_cast<WavePool*>(smem_blob + pool_offset);
+  WavePool& W = *reinterpret_cast<WavePool*>(smem_blob);
   SceneView sv;
   sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
   sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
@@ -1806,7 +1809,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     // ---- wavefront kernel: one CTA per SM, ray pool + (when it fits) the scan blob in shared memory
     // shared memory: the ray pool, and in front of it the scan blob with the side tables (else the blob alone, else nothing)
     const size_t pool_bytes = sizeof(WavePool);
-    auto with_pool = [&](size_t bytes) { return (bytes + 127u) / 128u * 128u + pool_bytes; };
+    auto with_pool = [&](size_t bytes) { return (pool_bytes + 127u) / 128u * 128u + bytes; };
     const long long most = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc);
     q.staged_bytes = (long long)with_pool(p.scene.stage_bytes) <= most  ? p.scene.stage_bytes
                      : (long long)with_pool(p.scene.blob_bytes) <= most ? p.scene.blob_bytes
