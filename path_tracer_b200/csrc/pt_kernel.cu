@@ -1350,9 +1350,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   if (tid < 8) W.counts[tid] = 0;
   if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
-  {
+  if (!express) {  // (an express CTA goes straight to the hand-off service, whose first source is its reserved tiles)
     // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
-    const int cap = express ? kExpressPool : p.pool_cap;
+    const int cap = p.pool_cap;
     for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
       const int slot = s0 + lane;
       bool alive = false;
@@ -1381,7 +1381,23 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       if (room > 0 && ((round & 7u) == 0u || waiting == 0)) {
         __syncthreads();  // everybody has read the two (and decided alike) before anybody changes them
         int got = -1;
-        if (tid < room) got = take_heavy();
+        if (tid < room) {
+          // an express CTA's first source is the head of the LPT order (reserved for it), then the hand-off queue -- which
+          // it serves from the start, whenever it has room
+          uint32_t pixq;
+          Rng rng;
+          int px, py;
+          if (express && next_pixel(pixq, rng, px, py)) {
+            const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
+            Ray ray;
+            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+            W.pix[slot] = pixq, W.scans[slot] = -1;  // (never handed off again)
+            W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
+          } else {
+            got = take_heavy();
+          }
+        }
         if (got >= 0) {
           const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
           const float* e = hq.entries + (size_t)got * kHeavyEntryWords;
