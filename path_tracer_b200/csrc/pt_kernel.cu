@@ -1846,7 +1846,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
     // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
-    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid + 3) / 7 : 0);  // 21 of 148: measured best on the default scene
+    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid * 23 + 100) / 200 : 0);  // 17 of 148: measured best on the default scene
     if (q.n_express >= grid) q.n_express = grid - 1;
     if (p.order_mode == 2) {
       q.n_express = 0;
