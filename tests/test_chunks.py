@@ -32,7 +32,8 @@ def chunk_layout(sc, t0, t1):
 
 
 CASES = [("c1", 0.0, 1.0), ("rtiow", 0.0, 0.0), ("moving", 0.0, 1.0), ("moving", -0.5, 2.5), ("motion_blur", 0.2, 0.4),
-         ("spheres_basic", 0.0, 0.0), ("media", 0.0, 1.0), ("random3", 0.0, 1.0)]
+         ("spheres_basic", 0.0, 0.0), ("media", 0.0, 1.0), ("random3", 0.0, 1.0), ("empty", 0.0, 0.0),
+         ("single_light", 0.0, 1.0), ("cornell", 0.0, 0.0)]
 
 
 @pytest.mark.parametrize("name,t0,t1", CASES)
