@@ -9,16 +9,22 @@ LIB := path_tracer_b200/lib/libptb200.so
 NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
            -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
            -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -I$(CSRC) $(PT_DEFS)
-SRCS := $(CSRC)/pt_kernel.cu $(CSRC)/pt_api.cu $(CSRC)/pt_pack.cpp
+SRCS := $(CSRC)/pt_wave.cu $(CSRC)/pt_lane.cu $(CSRC)/pt_api.cu $(CSRC)/pt_pack.cpp
+OBJS := $(patsubst $(CSRC)/%,build/obj/%.o,$(SRCS))
 HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/pt_abi.h
 
 all: lib oracle host
 
-lib: $(LIB)
+lib:
+	$(MAKE) -j4 $(LIB)
 
-$(LIB): $(SRCS) $(HDRS)
+build/obj/%.o: $(CSRC)/% $(HDRS)
+	mkdir -p build/obj
+	$(NVCC) $(NVFLAGS) -x cu -c -o $@ $<
+
+$(LIB): $(OBJS)
 	mkdir -p $(dir $(LIB))
-	$(NVCC) $(NVFLAGS) -shared -cudart static -o $@ $(SRCS)
+	$(NVCC) $(NVFLAGS) -shared -cudart static -o $@ $(OBJS)
 
 oracle:
 	$(MAKE) -C oracle

@@ -31,8 +31,8 @@ PT_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
 PT_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 PT_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
 #else
-__device__ __noinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
-__device__ __noinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+static __device__ __noinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+static __device__ __noinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
 #endif
 
 struct V3 {
@@ -66,11 +66,11 @@ PT_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {
 }
 
 // ---- transcendentals: binary64 evaluation, one rounding to binary32 -------
-__device__ __noinline__ float t_sin(float x) { return __double2float_rn(sin((double)x)); }
+static __device__ __noinline__ float t_sin(float x) { return __double2float_rn(sin((double)x)); }
 PT_DEV float t_cos(float x) { return __double2float_rn(cos((double)x)); }
 // Out-of-line (one copy in the kernel image; the scan loop must own the instruction
 // cache) and by value (nothing forced into local memory).
-__device__ __noinline__ float2 t_sincos2(float x) {
+static __device__ __noinline__ float2 t_sincos2(float x) {
   double ds, dc;
   sincos((double)x, &ds, &dc);
   return make_float2(__double2float_rn(ds), __double2float_rn(dc));
@@ -81,7 +81,7 @@ PT_DEV void t_sincos(float x, float& s, float& c) {
 }
 PT_DEV float t_asin(float x) { return __double2float_rn(asin((double)x)); }
 PT_DEV float t_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
-__device__ __noinline__ float t_log(float x) { return __double2float_rn(log((double)x)); }
+static __device__ __noinline__ float t_log(float x) { return __double2float_rn(log((double)x)); }
 // pow(x, 5.0f) (material.hpp:65): x^5 by binary64 products (4 roundings at 2^-53)
 PT_DEV float t_pow5(float x) {
   const double d = (double)x;

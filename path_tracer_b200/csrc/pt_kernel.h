@@ -71,6 +71,8 @@ cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h,
 int max_smem_blob_bytes(int device);
 cudaError_t launch_render(const RenderParams& p, int device, int grid_override, cudaStream_t stream,
                           LaunchInfo* info);
+// the lane kernel's launch (pt_lane.cu); launch_render() dispatches to it for kernel_kind == 1
+cudaError_t launch_lane(const RenderParams& p, int device, int grid_override, cudaStream_t stream, LaunchInfo* info);
 
 }  // namespace ptb
 #endif

@@ -1,0 +1,517 @@
+// pt_prims.cuh -- the closest-hit scan of render.hpp:30-51: primitives (sphere / rect / triangle / box /
+// constant_medium, each in the reference's operation order), the conservative sphere miss filter, chunk
+// culling, and the per-ray scan drivers shared by both kernels.  Parity-critical: everything here is
+// exercised bit for bit against the oracle; the schedulers (pt_wave.cu, pt_lane.cu) only decide which
+// lane runs which piece.
+#ifndef PT_PRIMS_CUH
+#define PT_PRIMS_CUH
+#include <stdint.h>
+
+#include "pt_abi.h"
+#include "pt_device.cuh"
+#include "pt_packed.h"
+#include "pt_stage.cuh"
+
+namespace ptb {
+namespace {
+
+constexpr float kTMin = 0.001f;  // render.hpp:40
+#ifndef PT_SCAN_UNROLL
+#define PT_SCAN_UNROLL 8
+#endif
+constexpr int kScanUnroll = PT_SCAN_UNROLL;  // spheres per hot-loop trip
+#ifndef PT_DEEP_RATE
+#define PT_DEEP_RATE 20
+#endif
+constexpr int kDeepRate = PT_DEEP_RATE;  // lane kernel: a pixel is DEEP above kDeepBase + kDeepRate * samples scans so far
+constexpr int kDeepBase = 64;
+#ifndef PT_MIN_PIXELS_PER_TEAM
+#define PT_MIN_PIXELS_PER_TEAM 3
+#endif
+constexpr int kMinPixelsPerTeam = PT_MIN_PIXELS_PER_TEAM;  // launch with larger teams below this many pixels per team
+
+struct Best {
+  float t;
+  int id;
+};
+
+// Tie-break keys of every object (pt_packed.h); small enough to travel by value into out-of-line code.
+struct KeyTable {
+  const int32_t* keys;
+  uint32_t base[6];
+};
+PT_DEV KeyTable key_table(const SceneDesc& sc) {
+  KeyTable k;
+  k.keys = sc.keys;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) k.base[i] = sc.key_base[i];
+  return k;
+}
+PT_DEV int key_of(const KeyTable& kt, int id) {
+  const int type = id >> kIdShift;
+  uint32_t b = kt.base[0];
+#pragma unroll
+  for (int i = 1; i < 6; ++i)
+    if (type == i) b = kt.base[i];
+  return kt.keys[b + (uint32_t)(id & (int)kIdMask)];
+}
+PT_DEV int key_of(const SceneDesc& sc, int id) {
+  return sc.keys[sc.key_base[id >> kIdShift] + (uint32_t)(id & (int)kIdMask)];
+}
+
+// Winner rule: minimum t, then maximum key (pt_packed.h).  Called with a
+// candidate that already satisfies its own primitive's range test.
+template <typename Keys> PT_DEV void consider(const Keys& sc, Best& best, float t, int id) {
+  if (t < best.t) {
+    best.t = t, best.id = id;
+  } else if (t == best.t) {
+    if (best.id < 0 || key_of(sc, id) > key_of(sc, best.id)) best.t = t, best.id = id;
+  }
+}
+// rect / triangle / box accept with `!(t > max)`, which lets NaN through
+// (rectangle.hpp:36, triangle.hpp:91): mirror that.
+template <typename Keys> PT_DEV void consider_le(const Keys& sc, Best& best, float t, int id) {
+  if (t == best.t) {
+    if (best.id < 0 || key_of(sc, id) > key_of(sc, best.id)) best.id = id;
+  } else {
+    best.t = t, best.id = id;
+  }
+}
+
+// ---------------------------------------------------------------- primitives
+// Exact roots of one sphere for the scan (sphere.hpp:74-105 with max = +inf;
+// the running-closest filter is applied by consider()).  `a` = dot(d,d).
+template <typename Keys>
+PT_DEV void sphere_roots_scan(const Keys& sc, Best& best, const Ray& r, float a, float cx, float cy, float cz, float r2,
+                              int id) {
+  const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
+  const float b = fadd(fadd(fmul(ocx, r.d.x), fmul(ocy, r.d.y)), fmul(ocz, r.d.z));
+  const float c = fsub(fadd(fadd(fmul(ocx, ocx), fmul(ocy, ocy)), fmul(ocz, ocz)), r2);
+  const float disc = fsub(fmul(b, b), fmul(a, c));
+  if (!(disc > 0.f)) return;
+  // Both roots are <= 0 < t_min when the centre is behind an outside origin:
+  // c > 0 gives sqrt(disc) <= b, so (-b + sqrt(disc))/a <= 0.
+  if (b > 0.f && c > 0.f) return;
+  const float sq = fsqrt(disc);
+  const float t0 = fdiv(fsub(-b, sq), a);
+  if (t0 < kInf && t0 > kTMin) {
+    consider(sc, best, t0, id);
+    return;
+  }
+  const float t1 = fdiv(fadd(-b, sq), a);
+  if (t1 < kInf && t1 > kTMin) consider(sc, best, t1, id);
+}
+
+// sphere.hpp:59-106 in full, for constant_medium boundaries (arbitrary min/max).
+PT_DEV bool sphere_hit_t(const Ray& r, V3 center, float r2, float tmin, float tmax, float& t_out) {
+  const V3 oc = vsub(r.o, center);
+  const float a = vdot(r.d, r.d);
+  const float b = vdot(oc, r.d);
+  const float c = fsub(vdot(oc, oc), r2);
+  const float disc = fsub(fmul(b, b), fmul(a, c));
+  if (disc > 0.f) {
+    const float sq = fsqrt(disc);
+    float temp = fdiv(fsub(-b, sq), a);
+    if (temp < tmax && temp > tmin) {
+      t_out = temp;
+      return true;
+    }
+    temp = fdiv(fadd(-b, sq), a);
+    if (temp < tmax && temp > tmin) {
+      t_out = temp;
+      return true;
+    }
+  }
+  return false;
+}
+
+struct AxisSel {
+  float ok, dk, oa, da, ob, db;
+};
+PT_DEV AxisSel axis_select(const Ray& r, int axis) {
+  if (axis == PT_AXIS_XY) return AxisSel { r.o.z, r.d.z, r.o.x, r.d.x, r.o.y, r.d.y };
+  if (axis == PT_AXIS_XZ) return AxisSel { r.o.y, r.d.y, r.o.x, r.d.x, r.o.z, r.d.z };
+  return AxisSel { r.o.x, r.d.x, r.o.y, r.d.y, r.o.z, r.d.z };
+}
+
+// rectangle.hpp:31-49 / 69-87 / 107-125: returns hit and t (a, b = in-plane coordinates).
+PT_DEV bool rect_hit_t(const Ray& r, int axis, float a0, float a1, float b0, float b1, float k, float tmin,
+                       float tmax, float& t_out, float& a_out, float& b_out) {
+  const AxisSel s = axis_select(r, axis);
+  const float t = fdiv(fsub(k, s.ok), s.dk);
+  if (t < tmin || t > tmax) return false;
+  const float a = fadd(s.oa, fmul(t, s.da));
+  const float b = fadd(s.ob, fmul(t, s.db));
+  if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+  t_out = t, a_out = a, b_out = b;
+  return true;
+}
+
+// box.hpp:29-50 over the six sides of box.hpp:20-25 (xy@p1.z, xy@p0.z, xz@p1.y, xz@p0.y, yz@p1.x,
+// yz@p0.x; a later side takes a tie).  Returns the winning side or -1.  One loop body instead of six
+// inlined rectangles keeps the code small.
+PT_DEV bool box_side_hit_t(const Ray& r, V3 p0, V3 p1, int s, float tmin, float tmax, float& t, float& a, float& b) {
+  const int axis = s >> 1;  // PT_AXIS_XY, PT_AXIS_XZ, PT_AXIS_YZ
+  const bool hi = (s & 1) == 0;
+  float a0, a1, b0, b1, k;
+  if (axis == PT_AXIS_XY)
+    a0 = p0.x, a1 = p1.x, b0 = p0.y, b1 = p1.y, k = hi ? p1.z : p0.z;
+  else if (axis == PT_AXIS_XZ)
+    a0 = p0.x, a1 = p1.x, b0 = p0.z, b1 = p1.z, k = hi ? p1.y : p0.y;
+  else
+    a0 = p0.y, a1 = p1.y, b0 = p0.z, b1 = p1.z, k = hi ? p1.x : p0.x;
+  return rect_hit_t(r, axis, a0, a1, b0, b1, k, tmin, tmax, t, a, b);
+}
+PT_DEV int box_hit_t(const Ray& r, V3 p0, V3 p1, float tmin, float tmax, float& t_out, float& a_out,
+                     float& b_out) {
+  int side = -1;
+  float closest = tmax;
+#pragma unroll 1
+  for (int s = 0; s < 6; ++s) {
+    float t, a, b;
+    if (box_side_hit_t(r, p0, p1, s, tmin, closest, t, a, b)) side = s, closest = t, t_out = t, a_out = a, b_out = b;
+  }
+  return side;
+}
+
+// triangle.hpp:58-100 (Moller-Trumbore) up to the range test; e1, e2 hoisted.
+PT_DEV bool triangle_hit_t(const Ray& r, V3 v0, V3 e1, V3 e2, float tmin, float tmax, float& t_out) {
+  const V3 h = vcross(r.d, e2);
+  const float a = vdot(e1, h);
+  const float a_abs = fabsf(a);
+  if (a_abs < 0.0000001f) return false;
+  const bool a_pos = a > 0.f;
+  const V3 s = vsub(r.o, v0);
+  const float u = vdot(s, h);
+  const bool u_pos = u > 0.f;
+  if ((u_pos != a_pos) || fabsf(u) > a_abs) return false;
+  const V3 q = vcross(s, e1);
+  const float v = vdot(r.d, q);
+  const bool v_pos = v > 0.f;
+  if ((v_pos != a_pos) || (fabsf(fadd(u, v)) > a_abs)) return false;
+  const float length = fdiv(vdot(e2, q), a);
+  if (length < tmin || length > tmax) return false;
+  t_out = length;
+  return true;
+}
+
+PT_DEV V3 moving_center(V3 c0, V3 dv, float f) { return vadd(c0, vscale(f, dv)); }  // sphere.hpp:55
+
+// constant_medium.hpp:28-78.  Draws one RNG number iff both boundary hits
+// succeed and rec1.t < rec2.t after clipping.
+PT_DEV bool medium_hit_t(const MediumRec& m, const Ray& r, float tmin, float tmax, Rng& rng, float& t_out) {
+  float t1, t2;
+  if (m.boundary_kind == PT_BOUNDARY_SPHERE) {
+    V3 center = vld(m.c0);
+    if (m.moving) center = moving_center(center, vld(m.dv), fdiv(fsub(r.tm, m.time0), m.den));
+    if (!sphere_hit_t(r, center, m.r2, -kInf, kInf, t1)) return false;
+    if (!sphere_hit_t(r, center, m.r2, fadd(t1, 0.0001f), kInf, t2)) return false;
+  } else {
+    float a, b;
+    const V3 p0 = vld(m.p0), p1 = vld(m.p1);
+    if (box_hit_t(r, p0, p1, -kInf, kInf, t1, a, b) < 0) return false;
+    if (box_hit_t(r, p0, p1, fadd(t1, 0.0001f), kInf, t2, a, b) < 0) return false;
+  }
+  if (t1 < tmin) t1 = tmin;
+  if (t2 > tmax) t2 = tmax;
+  if (t1 >= t2) return false;
+  if (t1 < 0.f) t1 = 0.f;
+  const float ray_length = vlength(r.d);
+  const float distance_inside_boundary = fmul(fsub(t2, t1), ray_length);
+  const float hit_distance = fmul(m.neg_inv_density, t_log(rng_float(rng)));
+  if (hit_distance > distance_inside_boundary) return false;
+  t_out = fadd(t1, fdiv(hit_distance, ray_length));
+  return true;
+}
+
+// ---------------------------------------------------------------- the scan
+// Merge the members' partial winners: afterwards every member of a team holds the team's winner.
+PT_DEV void team_merge(const SceneDesc& sc, Best& best, int team_size) {
+  for (int o = team_size >> 1; o > 0; o >>= 1) {
+    const float ot = __shfl_xor_sync(0xffffffffu, best.t, o);
+    const int oid = __shfl_xor_sync(0xffffffffu, best.id, o);
+    if (oid >= 0) {
+      if (best.id < 0 || ot < best.t)
+        best.t = ot, best.id = oid;
+      else if (ot == best.t && oid != best.id && key_of(sc, oid) > key_of(sc, best.id))
+        best.id = oid;
+    }
+  }
+}
+
+// Two-phase sphere test.  Phase 1 is branch-free and only collects a bitmask of spheres whose
+// discriminant is positive; phase 2 computes exact roots for the set bits.
+// Centre of the sphere at slot `p` ({c, r*r} entry; a moving sphere's {c1 - c0} is 32 entries further,
+// pt_packed.h) at the ray's time (sphere.hpp:51-56), exactly as the reference computes it.
+template <bool kSmem, bool kMoving>
+PT_DEV void sphere_center(const float4* __restrict__ p, float f, float& cx, float& cy, float& cz, float& r2_filter) {
+  const float4 s = ld4<kSmem>(p);
+  if constexpr (kMoving) {
+    const float4 v = ld4<kSmem>(p + 2 * kSphereChunk);
+    cx = fadd(s.x, fmul(f, v.x)), cy = fadd(s.y, fmul(f, v.y)), cz = fadd(s.z, fmul(f, v.z)), r2_filter = s.w;  // sphere.hpp:55
+  } else {
+    cx = s.x, cy = s.y, cz = s.z, r2_filter = s.w;
+  }
+}
+
+// CONSERVATIVE MISS FILTER (the hot instruction sequence of the whole renderer).  The reference
+// evaluates  disc = b*b - a*c,  b = dot(oc, d),  c = dot(oc, oc) - r*r  with 17 separately rounded
+// operations and hits only if disc > 0 (sphere.hpp:68-74).  Parity needs that exact sequence ONLY
+// for spheres that can be hit; for the others it is enough to PROVE disc <= 0.  The filter
+// evaluates, with fused multiply-adds (11 operations),
+//     test = b'^2 - a(1-k) * (|oc|^2 - r^2 (1+e)),   e = 2k / (1-k)
+// which in exact arithmetic equals  disc + k * a * (|oc|^2 + r^2).  Either evaluation is within
+// 13 u a (|oc|^2 + r^2) of the exact real value (u = 2^-24; error analysis in DESIGN.md), so with
+// k = 4e-6 > 27 u the implication  (reference disc > 0)  =>  (test > 0)  always holds: the filter never
+// drops a sphere the reference would hit.  Spheres that pass are re-evaluated with the exact
+// sequence (sphere_roots_scan), so false positives only cost time.  The blob stores r^2 (1+e)
+// (rounded up); the exact r*r comes from the side table.
+constexpr float kFilterK = 4.0e-6f;
+PT_DEV float filter_a(float a) { return fmul(a, 1.0f - kFilterK); }
+// Returns the bits of -test: the SIGN BIT is set for every sphere the filter lets through (and, harmlessly,
+// for -0 and some NaNs), so the per-lane candidate mask is collected with one funnel shift per sphere.
+template <bool kSmem, bool kMoving>
+PT_DEV uint32_t sphere_filter_bits(const float4* __restrict__ p, float f, const Ray& r, float a_filter) {
+  float cx, cy, cz, r2f;
+  sphere_center<kSmem, kMoving>(p, f, cx, cy, cz, r2f);
+  const float ocx = fsub(r.o.x, cx), ocy = fsub(r.o.y, cy), ocz = fsub(r.o.z, cz);
+  const float b = __fmaf_rn(ocx, r.d.x, __fmaf_rn(ocy, r.d.y, fmul(ocz, r.d.z)));
+  const float c = __fmaf_rn(ocx, ocx, __fmaf_rn(ocy, ocy, __fmaf_rn(ocz, ocz, -r2f)));
+  return __float_as_uint(__fmaf_rn(-b, b, fmul(a_filter, c)));
+}
+PT_DEV float exact_r2(const SphereAux* aux, int i) {
+  const float radius = aux[i].radius;
+  return fmul(radius, radius);  // sphere.hpp:71
+}
+
+// CHUNK CULLING.  Spheres come in chunks of 16 spatially close ones, each with a bounding box
+// (pt_packed.h); a ray scans only the chunks whose box it crosses between t = 0 and the running
+// closest hit.  The result is the reference's for ANY set of skipped chunks that cannot contain an
+// accepted root (the winner rule is order independent), so what has to hold is: "the reference accepts
+// a root of sphere i" => "the box test of i's chunk passes".  The boxes are grown on the host by a
+// margin that covers the rounding of the reference's own root, of the centre and of this slab test
+// for every origin with max |coordinate| <= cull_bound[set] (pt_pack.cpp, DESIGN.md "chunk
+// culling"); the last set is infinite boxes and serves every other ray.  The slab test runs on
+// 1/d clamped to +-2^60: for a component below 2^-60 the plane distances then come out within
+// t / 2^60 of zero instead of exactly there, far inside the margin, as long as the direction's largest
+// component lies in [2^-20, 2^20] -- rays outside that range are not culled at all.
+struct CullRay {
+  float ix, iy, iz;  // clamped 1 / d
+  float qx, qy, qz;  // -o * (1 / d)
+};
+constexpr float kCullInvMax = 1.152921504606847e18f;  // 2^60
+constexpr float kCullDirMin = 9.5367431640625e-7f;    // 2^-20
+constexpr float kCullDirMax = 1048576.f;              // 2^20
+PT_DEV float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Returns the box set of this ray.
+PT_DEV int make_cull_ray(const SceneDesc& sc, const Ray& r, CullRay& c) {
+  const float dmax = fmaxf(fmaxf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z));
+  const float omax = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z));
+  int set = (kCullSets - 1) - ((omax <= sc.cull_bound[0]) + (omax <= sc.cull_bound[1]) + (omax <= sc.cull_bound[2]));
+  if (!(dmax >= kCullDirMin && dmax <= kCullDirMax)) set = kCullSets - 1;
+  c.ix = fminf(fmaxf(rcp_fast(r.d.x), -kCullInvMax), kCullInvMax);
+  c.iy = fminf(fmaxf(rcp_fast(r.d.y), -kCullInvMax), kCullInvMax);
+  c.iz = fminf(fmaxf(rcp_fast(r.d.z), -kCullInvMax), kCullInvMax);
+  c.qx = -(r.o.x * c.ix), c.qy = -(r.o.y * c.iy), c.qz = -(r.o.z * c.iz);
+  return set;
+}
+// Bits of (entry - exit) of the ray's interval inside the box, clipped to [0, tmax]: SIGN BIT set <=>
+// the ray crosses the box there (fminf / fmaxf drop NaNs, which only ever widens the interval).
+template <bool kSmem> PT_DEV uint32_t chunk_bits(const float4* __restrict__ box, const CullRay& c, float tmax) {
+  const float4 lo = ld4<kSmem>(box), hi = ld4<kSmem>(box + 1);
+  const float ax = __fmaf_rn(lo.x, c.ix, c.qx), bx = __fmaf_rn(hi.x, c.ix, c.qx);
+  const float ay = __fmaf_rn(lo.y, c.iy, c.qy), by = __fmaf_rn(hi.y, c.iy, c.qy);
+  const float az = __fmaf_rn(lo.z, c.iz, c.qz), bz = __fmaf_rn(hi.z, c.iz, c.qz);
+  const float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+  const float t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+  return __float_as_uint(t_in - t_out);
+}
+
+// Bitmask of the chunks cb .. cb + nb - 1 (nb <= 32) whose box the ray crosses before tmax: chunk cb + k at
+// bit nb - 1 - k.  Same box for every lane: broadcast loads.
+template <bool kSmem>
+PT_DEV uint32_t chunk_hits(const float4* __restrict__ boxes, int cb, int nb, const CullRay& cr, float tmax) {
+  uint32_t hits = 0;
+#pragma unroll 2
+  for (int k = 0; k < nb; ++k) hits = __funnelshift_l(chunk_bits<kSmem>(boxes + 2 * (cb + k), cr, tmax), hits, 1);
+  return hits;
+}
+
+// Filter + exact roots of kOwn spheres of one chunk: slots p, p + kStep, ... of the doubled chunk, where
+// p = chunk base + rot0 (pt_packed.h).  Lanes of a warp work on DIFFERENT chunks at the same time; with
+// rot0 = (lane & 15) + const they read different shared-memory banks.
+template <bool kSmem, bool kMoving, int kOwn, int kStep, typename Keys>
+PT_DEV void scan_chunk(const Keys& sc, const float4* __restrict__ data, const SphereAux* aux, int chunk, int rot0,
+                       const Ray& r, float a, float af, float f, int type, Best& best) {
+  constexpr int kUnroll = kOwn < kScanUnroll ? kOwn : kScanUnroll;
+  constexpr int kSlots = kMoving ? 4 * kSphereChunk : 2 * kSphereChunk;  // float4 per chunk
+  const float4* base = data + chunk * kSlots + rot0;
+  uint32_t mask = 0;  // own k-th sphere at bit kOwn - 1 - k
+#pragma unroll 1
+  for (int it = 0; it < kOwn; it += kUnroll) {
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j)
+      mask = __funnelshift_l(sphere_filter_bits<kSmem, kMoving>(base + (it + j) * kStep, f, r, af), mask, 1);
+  }
+  while (mask) {
+    const int mt = 31 - __clz((int)mask);
+    mask &= ~(1u << mt);
+    const int k = kOwn - 1 - mt;
+    const int i = chunk * kSphereChunk + ((rot0 + k * kStep) & (kSphereChunk - 1));
+    float cx, cy, cz, r2f;
+    sphere_center<kSmem, kMoving>(base + k * kStep, f, cx, cy, cz, r2f);
+    sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
+  }
+}
+
+// Scan the chunks [first_el / 16, end_el / 16) of one sphere group for one ray, kTeam lanes per ray: every
+// lane first collects the bitmask of chunks the ray crosses, then pops its next chunk and filters its
+// share of the 16 spheres (own k-th sphere = slot rot + k * kTeam, rot = lane & 15).
+template <bool kSmem, bool kMoving, int kTeam, typename Keys>
+PT_DEV void scan_sphere_chunks(const Keys& sc, const float4* __restrict__ data, const float4* __restrict__ boxes,
+                               const SphereAux* aux, int first_el, int end_el, int rot, const Ray& r, float a,
+                               float f, const CullRay& cr, bool act, int type, Best& best) {
+  const float af = filter_a(a);
+  const int c_end = end_el / kSphereChunk;
+#pragma unroll 1
+  for (int cb = first_el / kSphereChunk; cb < c_end; cb += 32) {
+    const int nb = min(32, c_end - cb);
+    float tmax = act ? best.t : -1.f;
+    uint32_t hits = 0;  // chunk cb + k at bit nb - 1 - k
+    if constexpr (kTeam == 1) {
+      hits = chunk_hits<kSmem>(boxes, cb, nb, cr, tmax);
+    } else {
+      // The team shares the box tests: member m takes chunks m, m + kTeam, ... against the smallest of the
+      // members' running closest hits, and the members' bits are OR-ed together (the whole warp is
+      // converged here: the loop bounds depend on the group only).
+#pragma unroll
+      for (int o = kTeam >> 1; o > 0; o >>= 1) tmax = fminf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+#pragma unroll 1
+      for (int k = rot & (kTeam - 1); k < nb; k += kTeam)
+        hits |= (chunk_bits<kSmem>(boxes + 2 * (cb + k), cr, tmax) >> 31) << (nb - 1 - k);
+#pragma unroll
+      for (int o = kTeam >> 1; o > 0; o >>= 1) hits |= __shfl_xor_sync(0xffffffffu, hits, o);
+    }
+#pragma unroll 1
+    while (hits) {
+      const int top = 31 - __clz((int)hits);
+      hits &= ~(1u << top);
+      scan_chunk<kSmem, kMoving, kSphereChunk / kTeam, kTeam>(sc, data, aux, cb + (nb - 1 - top), rot, r, a, af, f, type, best);
+    }
+  }
+}
+
+// The team variants (kTeam lanes share a ray, each with its own partial winner): out of line and by
+// value, so that they do not sit between the hot loops in the instruction stream.
+template <bool kSmem, bool kMoving>
+__device__ __noinline__ Best scan_spheres_team(KeyTable sc, const float4* __restrict__ data,
+                                               const float4* __restrict__ boxes, const SphereAux* aux, int first_el,
+                                               int end_el, int team_size, Ray r, float a, float f, CullRay cr, bool act,
+                                               int type, Best best) {
+  const int rot = (int)(threadIdx.x & (kSphereChunk - 1));
+  switch (team_size) {
+    case 2: scan_sphere_chunks<kSmem, kMoving, 2>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+    case 4: scan_sphere_chunks<kSmem, kMoving, 4>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+    case 8: scan_sphere_chunks<kSmem, kMoving, 8>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+    default: scan_sphere_chunks<kSmem, kMoving, 16>(sc, data, boxes, aux, first_el, end_el, rot, r, a, f, cr, act, type, best); break;
+  }
+  return best;
+}
+
+template <bool kSmem, bool kMoving>
+PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, const float4* __restrict__ boxes,
+                         const SphereAux* aux, int first_el, int end_el, int team_size, const Ray& r, float a, float f,
+                         const CullRay& cr, bool act, int type, Best& best) {
+  if (team_size == 1)
+    scan_sphere_chunks<kSmem, kMoving, 1>(sc, data, boxes, aux, first_el, end_el, (int)(threadIdx.x & (kSphereChunk - 1)),
+                                          r, a, f, cr, act, type, best);
+  else
+    best = scan_spheres_team<kSmem, kMoving>(key_table(sc), data, boxes, aux, first_el, end_el, team_size, r, a, f, cr,
+                                             act, type, best);
+}
+
+// Rectangles, triangles and boxes of one group: elements first, first + step, ... (running closest as the
+// upper bound, like the reference's loop).
+template <bool kSmem>
+PT_DEV void scan_flat_group(const SceneDesc& sc, const SceneView& sv, const Group& g, const Ray& r, int first, int step,
+                            Best& best) {
+  const int end = g.begin + g.count;
+  if (g.type == G_RECT) {
+    for (int i = first; i < end; i += step) {
+      const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
+      const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
+      float t, ra, rb;
+      if (rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, best.t, t, ra, rb))
+        consider_le(sc, best, t, make_id(G_RECT, i));
+    }
+  } else if (g.type == G_TRIANGLE) {
+    for (int i = first; i < end; i += step) {
+      const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
+      const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
+      const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
+      float t;
+      if (triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, best.t, t))
+        consider_le(sc, best, t, make_id(G_TRIANGLE, i));
+    }
+  } else if (g.type == G_BOX) {
+    for (int i = first; i < end; i += step) {
+      const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
+      const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
+      float t, ra, rb;
+      if (box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, best.t, t, ra, rb) >= 0)
+        consider_le(sc, best, t, make_id(G_BOX, i));
+    }
+  }
+}
+
+// render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
+// of each group.  `act`: this lane's team carries a real ray (the others ride along so that the
+// warp stays converged on the shared loads and the shuffles).
+template <bool kSmem>
+PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, bool act, int member,
+                        int team_size) {
+  Best best { kInf, -1 };
+  const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant
+  CullRay cr;
+  const int cull_set = make_cull_ray(sc, r, cr);
+  const float4* sphere_boxes = sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
+  const float4* moving_boxes = sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks;
+  const int n_groups = (int)sc.n_groups;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const Group g = sv.groups[gi];
+    const int end = g.begin + g.count;
+    switch (g.type) {
+      case G_SPHERE:
+        scan_spheres<kSmem, false>(sc, sv.sphere, sphere_boxes, sc.sphere_aux, g.begin, end, team_size, r, a, 0.f, cr, act,
+                                   G_SPHERE, best);
+        break;
+      case G_MOVING_SPHERE:
+        scan_spheres<kSmem, true>(sc, sv.moving, moving_boxes, sc.moving_aux, g.begin, end, team_size, r, a,
+                                  fdiv(fsub(r.tm, g.time0), g.den), cr, act, G_MOVING_SPHERE, best);
+        break;
+      case G_MEDIUM: {
+        // G_MEDIUM sees the running closest hit of EVERY lower-index object (merge first) and commits
+        // unconditionally; every member replays the RNG draw on its replica of the generator.
+        if (team_size > 1) team_merge(sc, best, team_size);
+        if (act) {
+          float t;
+          if (medium_hit_t(sc.media[g.begin], r, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
+        }
+        break;
+      }
+      default:
+        if (act) scan_flat_group<kSmem>(sc, sv, g, r, g.begin + member, team_size, best);
+        break;
+    }
+  }
+  if (team_size > 1) team_merge(sc, best, team_size);
+  return best;
+}
+
+}  // namespace
+}  // namespace ptb
+#endif

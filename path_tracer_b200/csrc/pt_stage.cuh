@@ -1,0 +1,73 @@
+// pt_stage.cuh -- shared-memory staging (cp.async.bulk + mbarrier) and the kernels' view of the scan blob.
+#ifndef PT_STAGE_CUH
+#define PT_STAGE_CUH
+#include <stdint.h>
+
+#include "pt_device.cuh"
+#include "pt_packed.h"
+
+namespace ptb {
+namespace {
+
+PT_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
+
+PT_DEV unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---------------------------------------------------------------- staging
+PT_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PT_DEV void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+PT_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+PT_DEV void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+PT_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- scene view
+struct SceneView {
+  const Group* groups;
+  const float4* sphere;
+  const float4* moving;
+  const float4* rect;
+  const float4* triangle;
+  const float4* box;
+  const float4* sphere_box;  // chunk boxes, set 0 first
+  const float4* moving_box;
+};
+
+template <bool kSmem> PT_DEV float4 ld4(const float4* p) {
+  if constexpr (kSmem)
+    return *p;
+  else
+    return __ldg(p);
+}
+
+}  // namespace
+}  // namespace ptb
+#endif

@@ -1,0 +1,920 @@
+// pt_wave.cu -- the default render kernel: a bulk-synchronous wavefront inside one CTA per SM
+// (reference include/render.hpp:25-106 and everything it calls, re-scheduled for sm_100a).
+//
+// Execution model (B200-first, not a translation of the SYCL kernel):
+//   * A pixel's `spp` samples are inherently serial -- its xorshift32 stream is consumed in a
+//     data-dependent way (render.hpp:95-101) -- so the unit of work is a PIXEL, pulled from a global
+//     atomic queue; a finished pixel is replaced at once ("path regeneration").  Parallelism is
+//     pixels x objects.
+//   * The scene's scan blob (pt_packed.h) and its side tables are staged into shared memory with
+//     cp.async.bulk (TMA) once per CTA.  Objects come in k-d ordered CHUNKS behind conservative bounding
+//     boxes; a ray only looks at the chunks whose box it crosses (pt_prims.cuh: a proof, the result is
+//     bit-identical with and without it).
+//   * The winner of a scan is (minimum t, then maximum key), which reproduces the sequential scan's tie
+//     behaviour for ANY visiting order (pt_packed.h): that is what allows skipping chunks, splitting a
+//     scan over lanes or work items, and merging with shuffles or one 64-bit atomicMin.
+//   * One 896-thread CTA per SM, the path state of 896 pixels in a structure-of-arrays pool in shared
+//     memory, phases BOXES / ITEMS / LATE / SHADE separated by __syncthreads(); the closest-hit scan runs
+//     as (ray, chunk) work items spread over the whole CTA; shading runs in warps of one material kind.
+//     Deep pixels (paths bouncing dozens of times inside glass hold ten times the average work and would
+//     sit on a serial critical path) are traced by EXPRESS CTAs in short rounds, from the head of a
+//     longest-processing-time-first pixel order and from a global hand-off queue.
+// All arithmetic follows the operation order of the reference; see pt_device.cuh for the numerics contract.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pt_abi.h"
+#include "pt_device.cuh"
+#include "pt_kernel.h"
+#include "pt_packed.h"
+#include "pt_prims.cuh"
+#include "pt_shade.cuh"
+
+namespace ptb {
+
+namespace {
+// ---------------------------------------------------------------- the wavefront kernel
+// Bulk-synchronous wavefront inside one CTA per SM.  The path state of up to kWavePool pixels lives
+// in a structure-of-arrays RAY POOL in shared memory instead of in the registers of fixed lanes, and
+// the CTA alternates between phases separated by __syncthreads():
+//
+//   BOXES   one thread per ray: which sphere chunks does the ray cross (chunk culling, above)?  Every
+//           (ray, chunk) pair becomes a work ITEM in a CTA-wide list.
+//   SPHERES one thread per ITEM: the 16 spheres of the chunk against the ray; a hit is merged into the
+//           ray's winner with one 64-bit shared-memory atomicMin on {t, original object index} -- exactly
+//           the reference's rule for spheres (smallest t, then the earlier object, sphere.hpp:77,93).
+//           The work per item is the same whatever the ray, so the lanes of a warp stay busy although
+//           their rays cross different numbers of chunks, and a CTA with few rays left still has
+//           (rays x chunks) items to spread over its threads.
+//   LATE    one thread per ray: the groups from the first constant_medium on (flat objects and media in object
+//           order against the running closest hit), then what has to happen next -- background, or the kind of
+//           the hit material -- and the ray joins that kind's list ("compact divergent material work").
+//   SHADE   one warp per unit of up to 32 rays of ONE kind, so the lanes of a warp run the same material
+//           code; finished paths start their pixel's next sample (the RNG stream of a pixel is strictly
+//           serial) or write the pixel and pull a new one from the global pixel queue.
+// A scene with spheres BEHIND a constant_medium in the object list is scanned sequentially per ray in
+// BOXES instead (the medium needs the running closest hit of everything before it, and what follows
+// needs the medium's).
+//
+// HAND-OFF QUEUE.  A pixel's samples are serial and a full round takes tens of microseconds, so the
+// few pixels that hold ten times the average work (paths bouncing dozens of times inside glass:
+// 3 000 scans where the mean is 260) would sit on a critical path longer than the whole frame, and
+// at the end of the frame every CTA would drain its own leftovers alone.  A pixel whose scan rate
+// marks it as HEAVY is therefore handed, with its complete path state, to a global queue.  It is
+// taken over by a CTA that runs SHORT rounds because it keeps only kExpressPool rays in flight: one
+// of a few EXPRESS CTAs that do nothing else, or any CTA whose own pixels have run out -- which also
+// balances the end of the frame across the whole GPU.  With few rays the phases switch to finer
+// work units (a ray's boxes in blocks of 8, a chunk's spheres in quarters).
+//
+// Results are bit-identical to the lane kernel: the same device functions are called on the same
+// per-pixel state, only the assignment of work to lanes differs.
+#ifndef PT_WAVE_THREADS
+#define PT_WAVE_THREADS 896
+#endif
+#ifndef PT_WAVE_BLOCKS_PER_SM
+#define PT_WAVE_BLOCKS_PER_SM 1
+#endif
+#ifndef PT_WAVE_ROUNDS
+#define PT_WAVE_ROUNDS 1
+#endif
+#ifndef PT_HEAVY_RATE
+#define PT_HEAVY_RATE 10
+#endif
+#ifndef PT_HEAVY_RATE_DRY
+#define PT_HEAVY_RATE_DRY 10
+#endif
+#ifndef PT_EXPRESS_POOL
+#define PT_EXPRESS_POOL 64
+#endif
+#ifndef PT_WAVE_ITEMS
+#define PT_WAVE_ITEMS 4096
+#endif
+constexpr int kWaveThreads = PT_WAVE_THREADS;
+constexpr int kWavePool = PT_WAVE_ROUNDS * kWaveThreads;  // pixels (rays) a CTA keeps in flight: whole scan passes
+constexpr int kWaveKinds = 6;                              // 0 = background, 1 + PT_MAT_* otherwise
+constexpr int kHeavyRate = PT_HEAVY_RATE;                  // heavy: more than kHeavyBase + rate * samples scans so far
+constexpr int kHeavyRateDry = PT_HEAVY_RATE_DRY;           // ... a lower bar once the pixel queue is dry (load sharing)
+constexpr int kHeavyBase = 64;
+constexpr int kExpressPool = PT_EXPRESS_POOL;              // rays in flight in a CTA that serves the hand-off queue
+constexpr int kWaveItems = PT_WAVE_ITEMS;                  // (ray, chunk) items per round; the overflow is scanned in place
+constexpr int kWaveItemsStatic = kWaveItems * 3 / 8;       // ... of static spheres (from the front of the list)
+constexpr int kWaveItemsMoving = kWaveItems - kWaveItemsStatic;  // ... of moving spheres (from the back)
+constexpr unsigned long long kNoHit64 = 0x7f800000ffffffffull;  // {t = +inf, no object}
+#ifndef PT_FINE_RAYS
+#define PT_FINE_RAYS 160
+#endif
+constexpr int kFineRays = PT_FINE_RAYS;  // at most this many rays in the round: finer work units (short rounds)
+#ifndef PT_FINE_BOXES
+#define PT_FINE_BOXES 8
+#endif
+constexpr int kFineBoxes = PT_FINE_BOXES;            // ... BOXES: a ray's chunks in blocks of this many
+constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in runs of this many
+constexpr int kMaxBoxBlocks = 64;
+constexpr int kMaxFlats = 256;
+static_assert(kWavePool <= 1024, "an item packs the pool slot into 10 bits");
+
+struct WavePool {
+  unsigned long long best64[kWavePool];  // SPHERES: {float bits of t, original object index} of the ray's winner
+  uint2 items[kWaveItems];               // {slot | chunk << 10, f bits}: static-sphere items from the front, moving from the back
+  float ox[kWavePool], oy[kWavePool], oz[kWavePool], dx[kWavePool], dy[kWavePool], dz[kWavePool], tm[kWavePool];
+  float hit_t[kWavePool];
+  int hit_id[kWavePool];
+  float att_x[kWavePool], att_y[kWavePool], att_z[kWavePool];
+  float acc_x[kWavePool], acc_y[kWavePool], acc_z[kWavePool];
+  uint32_t rng[kWavePool];
+  uint32_t pix[kWavePool];  // position of the pixel in the work queue
+  int sample[kWavePool];
+  int bounce[kWavePool];
+  int scans[kWavePool];               // closest-hit scans spent on the current pixel (< 0: taken over, never handed off again)
+  unsigned short list_a[kWavePool];   // rays to scan (unordered)
+  unsigned short list_k[kWaveKinds][kWavePool];  // the same rays by kind (what happens next), filled by LATE
+  unsigned short free_list[kWavePool];  // hand-off service: pool slots without a pixel
+  int counts[8];
+  int n_next;      // length of list_a being built
+  int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
+  int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
+  int free_count;
+  int pixel_dry;   // the pixel queue has run dry
+  int service;     // hand-off service: 0 = keep polling, 1 = every producer is done and the queue is empty
+  int n_blocks;    // fine BOXES: blocks of <= kFineBoxes chunks over all sphere groups (0: too many, coarse only)
+  int4 blocks[kMaxBoxBlocks];  // {group, first chunk, chunks, 0}
+  int n_flats;     // rectangles, triangles and boxes in FRONT of the first constant_medium: tested one thread per (ray, object)
+  int first_late_group;  // the first constant_medium's group (n_groups if none): from here on the scan is sequential per ray
+  int2 flats[kMaxFlats];  // {group type, element}
+};
+
+PT_DEV int material_of(const SceneDesc& sc, int id) {
+  const int idx = id & (int)kIdMask;
+  switch (id >> kIdShift) {
+    case G_SPHERE: return sc.sphere_aux[idx].material;
+    case G_MOVING_SPHERE: return sc.moving_aux[idx].material;
+    case G_RECT: return sc.rect_aux[idx].material;
+    case G_TRIANGLE: return sc.tri_aux[idx].material;
+    case G_BOX: return sc.box_aux[idx].material;
+    default: return sc.media[idx].material;
+  }
+}
+
+// A ray's winner as one 64-bit word whose UNSIGNED ORDER is the winner rule of pt_packed.h (smaller t, then larger
+// key): {float bits of t (t >= 0), 0x7fffffff - key}.  Spheres (key = -1 - object) give codes 0x80000000 + object,
+// the others (key = object) 0x7fffffff - object.  A NaN t orders behind +inf and is never taken.
+PT_DEV unsigned long long pack_winner(float t, int key) {
+  return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(0x7fffffffu - (uint32_t)key);
+}
+PT_DEV unsigned long long pack_sphere_winner(const SphereAux* aux, const Best& b) {
+  return pack_winner(b.t, aux[b.id & (int)kIdMask].key);
+}
+PT_DEV Best unpack_winner(const SceneDesc& sc, unsigned long long v) {
+  Best best;
+  const uint32_t code = (uint32_t)v;
+  best.t = __uint_as_float((uint32_t)(v >> 32));
+  best.id = code == 0xffffffffu ? -1 : sc.object_id[code >= 0x80000000u ? code - 0x80000000u : 0x7fffffffu - code];
+  return best;
+}
+
+}  // namespace
+
+template <bool kSmem>
+__global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wave_kernel(const RenderParams p) {
+  extern __shared__ __align__(16) unsigned char smem_blob[];
+  __shared__ __align__(8) uint64_t stage_bar;
+  __shared__ SceneDesc staged_scene;  // the scene descriptor with the staged tables' pointers redirected to shared memory
+
+  // dynamic shared memory: the ray pool first (at a compile-time offset, so that its accesses need no address arithmetic),
+  // then the staged part of the arena
+  constexpr uint32_t kPoolBytes = ((uint32_t)sizeof(WavePool) + 127u) & ~127u;
+  unsigned char* const smem_stage = smem_blob + kPoolBytes;
+  const unsigned char* blob_base = p.scene.blob;
+  const uint32_t staged = kSmem ? p.staged_bytes : 0u;  // the scan blob, and the side tables behind it when they fit too
+  if constexpr (kSmem) {
+    if (threadIdx.x == 0) mbar_init(&stage_bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&stage_bar, staged);
+      constexpr uint32_t kPiece = 32768;
+      for (uint32_t off = 0; off < staged; off += kPiece)
+        bulk_g2s(smem_stage + off, p.scene.blob + off, min(kPiece, staged - off), &stage_bar);
+    }
+    blob_base = smem_stage;
+  }
+  if (threadIdx.x == 0) {
+    staged_scene = p.scene;
+    const unsigned char* g0 = p.scene.blob;
+    auto redirect = [&](auto& ptr) {
+      const size_t off = (size_t)(reinterpret_cast<const unsigned char*>(ptr) - g0);
+      if (kSmem && off < (size_t)staged) ptr = reinterpret_cast<decltype(ptr + 0)>(smem_stage + off);
+    };
+    redirect(staged_scene.sphere_aux), redirect(staged_scene.moving_aux), redirect(staged_scene.rect_aux);
+    redirect(staged_scene.tri_aux), redirect(staged_scene.box_aux), redirect(staged_scene.media);
+    redirect(staged_scene.keys), redirect(staged_scene.object_id);
+    const unsigned char* mats = static_cast<const unsigned char*>(staged_scene.materials);
+    redirect(mats);
+    staged_scene.materials = mats;
+  }
+  __syncthreads();
+  if constexpr (kSmem) mbar_wait(&stage_bar, 0);
+  const SceneDesc& sc = staged_scene;
+  WavePool& W = *reinterpret_cast<WavePool*>(smem_blob);
+  SceneView sv;
+  sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
+  sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
+  sv.moving = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
+  sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
+  sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
+  sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
+  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
+  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
+
+  if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
+  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rot = lane & (kSphereChunk - 1);
+  const pt_camera& cam = p.cam;
+  const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
+  const unsigned lane_lt = (1u << lane) - 1u;
+  const HeavyQueue& hq = p.heavy;
+  const bool express = (int)blockIdx.x < p.n_express;  // this CTA only serves the hand-off queue
+  const bool sequential_scan = sc.n_late_sphere_groups != 0u;
+  const int n_groups = (int)sc.n_groups;
+  unsigned int n_scans = 0;
+
+  // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
+  // The first p.express_positions positions of the queue (the most expensive tiles of the LPT order) belong to the
+  // express CTAs, which trace them in short rounds from the start; everybody else begins behind them.
+  auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py) -> bool {
+    for (;;) {
+      if (*reinterpret_cast<volatile int*>(&W.pixel_dry)) return false;  // (a set-once flag; a stale 0 only costs one more atomic)
+      unsigned long long pos;
+      if (express) {
+        pos = atomicAdd(p.pixel_counter + 1, 1ull);
+        if (pos >= p.express_positions) {
+          atomicExch(&W.pixel_dry, 1);
+          return false;
+        }
+      } else {
+        pos = p.express_positions + atomicAdd(p.pixel_counter, 1ull);
+        if (pos >= p.n_positions) {
+          atomicExch(&W.pixel_dry, 1);
+          if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
+          return false;
+        }
+      }
+      float* unused;
+      if (!queue_pixel(p, pos, px, py, unused)) continue;  // a tile position outside the region
+      pixq = (uint32_t)pos;
+      // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+      rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+      if (p.order_mode == 2) rng.s = (rng.s * 2654435761u) | 1u;  // cost probe: a throw-away stream, never the pixel's
+      return true;
+    }
+  };
+  // Take the next entry of the hand-off queue: its index, or -1 when there is none right now.
+  auto take_heavy = [&]() -> int {
+    unsigned int h = ld_volatile_u32(hq.ctrl + 0);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+      const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
+      if (h >= t) return -1;
+      const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
+      if (seen == h) {
+        while (ld_volatile_u32(hq.ready + h) != hq.stamp) {
+          if (globaltimer_ns() > t_give_up) {
+            if (p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
+            return -1;
+          }
+          __nanosleep(100);
+        }
+        __threadfence();
+        return (int)h;
+      }
+      h = seen;
+    }
+    return -1;
+  };
+  // Append the live slots of this warp to the next scan list (one shared-memory atomic per warp).
+  auto append = [&](bool alive, bool own, int slot) {
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    const unsigned mo = __ballot_sync(0xffffffffu, alive && own);
+    if (m != 0u) {
+      int base = 0;
+      if (lane == 0) {
+        base = atomicAdd(&W.n_next, __popc(m));
+        if (mo != 0u) atomicAdd(&W.n_own, __popc(mo));
+      }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (alive) W.list_a[base + __popc(m & lane_lt)] = (unsigned short)slot;
+    }
+  };
+  auto store_ray = [&](int slot, const Ray& ray, V3 att, V3 acc, Rng rng, int bounce, int sample) {
+    W.ox[slot] = ray.o.x, W.oy[slot] = ray.o.y, W.oz[slot] = ray.o.z;
+    W.dx[slot] = ray.d.x, W.dy[slot] = ray.d.y, W.dz[slot] = ray.d.z, W.tm[slot] = ray.tm;
+    W.att_x[slot] = att.x, W.att_y[slot] = att.y, W.att_z[slot] = att.z;
+    W.acc_x[slot] = acc.x, W.acc_y[slot] = acc.y, W.acc_z[slot] = acc.z;
+    W.rng[slot] = rng.s, W.bounce[slot] = bounce, W.sample[slot] = sample;
+    W.best64[slot] = kNoHit64;
+  };
+  auto load_ray = [&](int slot) -> Ray {
+    Ray ray;
+    ray.o = v3(W.ox[slot], W.oy[slot], W.oz[slot]);
+    ray.d = v3(W.dx[slot], W.dy[slot], W.dz[slot]);
+    ray.tm = W.tm[slot];
+    return ray;
+  };
+  // BOXES for one ray and the chunks [cb, cb + nb) of one sphere group: every crossed chunk becomes an item;
+  // what does not fit into the item list is scanned here and now (`inl`).
+  auto emit_items = [&](int slot, const Ray& ray, const CullRay& cr, const float4* boxes, bool moving, int cb, int nb, float f,
+                        float a, Best& inl) {
+    uint32_t hits = chunk_hits<kSmem>(boxes, cb, nb, cr, kInf);
+    if (hits == 0u) return;
+    const int cnt = __popc(hits);
+    int at = atomicAdd(moving ? &W.n_items_m : &W.n_items_s, cnt);
+    // static items grow from the front, moving ones from the back, each within its fixed share of the list
+    while (hits) {
+      const int top = 31 - __clz((int)hits);
+      hits &= ~(1u << top);
+      const int chunk = cb + (nb - 1 - top);
+      if (at < (moving ? kWaveItemsMoving : kWaveItemsStatic)) {
+        W.items[moving ? kWaveItems - 1 - at : at] = make_uint2((uint32_t)slot | ((uint32_t)chunk << 10), __float_as_uint(f));
+      } else {
+        if (p.counters) atomicAdd(p.counters + 15, 1ull);  // stats: items scanned in place (tests check that it happens)
+        if (moving)
+          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
+        else
+          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
+      }
+      ++at;
+    }
+  };
+
+  int mode = 0;  // 0: this CTA's share of the pixel queue (none for an express CTA); 1: hand-off service
+  if (tid == 0) {
+    int nb = 0;
+    for (int gi = 0; gi < n_groups && nb >= 0; ++gi) {
+      const Group g = sv.groups[gi];
+      if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
+      const int c_end = (g.begin + g.count) / kSphereChunk;
+      for (int cb = g.begin / kSphereChunk; cb < c_end; cb += kFineBoxes) {
+        if (nb == kMaxBoxBlocks) {
+          nb = -1;
+          break;
+        }
+        W.blocks[nb++] = make_int4(gi, cb, min(kFineBoxes, c_end - cb), 0);
+      }
+    }
+    W.n_blocks = nb < 0 ? 0 : nb;
+    // the flat objects in front of the first medium (as many as fit; the rest stays with the sequential part)
+    int nf = 0, late = n_groups;
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const Group g = sv.groups[gi];
+      if (g.type == G_MEDIUM || ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && nf + 6 * g.count > kMaxFlats)) {
+        late = gi;
+        break;
+      }
+      if (g.type == G_RECT || g.type == G_TRIANGLE)
+        for (int i = 0; i < g.count; ++i) W.flats[nf++] = make_int2(g.type, g.begin + i);
+      if (g.type == G_BOX)  // a box is six independent sides (box.hpp:20-25): the closest side is the box's hit
+        for (int i = 0; i < g.count; ++i)
+          for (int side = 0; side < 6; ++side) W.flats[nf++] = make_int2(G_BOX | (side << 8), g.begin + i);
+    }
+    W.n_flats = nf, W.first_late_group = late;
+  }
+  if (tid < 8) W.counts[tid] = 0;
+  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
+  __syncthreads();
+  if (!express) {  // (an express CTA goes straight to the hand-off service, whose first source is its reserved tiles)
+    // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
+    const int cap = p.pool_cap;
+    for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
+      const int slot = s0 + lane;
+      bool alive = false;
+      if (slot < cap) {
+        uint32_t pixq;
+        Rng rng;
+        int px, py;
+        if (next_pixel(pixq, rng, px, py)) {
+          Ray ray;
+          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+          W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;  // (an express CTA never hands a pixel off)
+          alive = true;
+        }
+      }
+      append(alive, !express, slot);
+    }
+    __syncthreads();
+  }
+
+  for (unsigned int round = 0;; ++round) {
+    if (mode == 1) {
+      // ---- hand-off service: fill the free pool slots from the global queue (polled every 8th round: a poll is
+      // two round trips to L2, and these rounds are the frame's critical path)
+      const int room = W.free_count, waiting = W.n_next;
+      if (room > 0 && ((round & 7u) == 0u || waiting == 0)) {
+        __syncthreads();  // everybody has read the two (and decided alike) before anybody changes them
+        int got = -1;
+        if (tid < room) {
+          // an express CTA's first source is the head of the LPT order (reserved for it), then the hand-off queue -- which
+          // it serves from the start, whenever it has room
+          uint32_t pixq;
+          Rng rng;
+          int px, py;
+          if (express && next_pixel(pixq, rng, px, py)) {
+            const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
+            Ray ray;
+            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+            W.pix[slot] = pixq, W.scans[slot] = -1;  // (never handed off again)
+            W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
+          } else {
+            got = take_heavy();
+          }
+        }
+        if (got >= 0) {
+          const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
+          const float* e = hq.entries + (size_t)got * kHeavyEntryWords;
+          Ray ray;
+          ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
+          ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
+          ray.tm = __ldcg(e + 10);
+          store_ray(slot, ray, v3(__ldcg(e + 11), __ldcg(e + 12), __ldcg(e + 13)), v3(__ldcg(e + 14), __ldcg(e + 15), __ldcg(e + 16)),
+                    Rng { __float_as_uint(__ldcg(e + 1)) }, __float_as_int(__ldcg(e + 3)), __float_as_int(__ldcg(e + 2)));
+          W.pix[slot] = __float_as_uint(__ldcg(e + 0)), W.scans[slot] = -1;
+          W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
+          if (p.counters) {  // stats: how long did the pixel wait in the queue
+            const unsigned long long waited = (uint32_t)((uint32_t)globaltimer_ns() - __float_as_uint(__ldcg(e + 17)));
+            atomicAdd(p.counters + 12, waited), atomicMax(p.counters + 13, waited);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const int n = W.n_next;  // rays to trace this round
+    if (n == 0) {
+      if (mode == 0) {
+        // ---- no regular work (left): say so, then serve the hand-off queue until the whole GPU is finished
+        if (p.order_mode == 2) break;  // the cost probe hands nothing off
+        mode = 1;
+        for (int s = tid; s < kExpressPool; s += kWaveThreads) W.free_list[s] = (unsigned short)s;
+        if (tid == 0) {
+          W.free_count = kExpressPool;
+          __threadfence();
+          atomicAdd(hq.ctrl + 2, 1u);
+          if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
+        }
+        __syncthreads();
+        continue;
+      }
+      // idle: every producer is done and the queue is empty (or the watchdog fired) => nothing will ever arrive again
+      if (tid == 0)
+        W.service = ((ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
+                      ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap)) ||
+                     globaltimer_ns() > t_give_up)
+                        ? 1
+                        : 0;
+      __syncthreads();
+      if (W.service == 1) break;
+      __nanosleep(300);
+      continue;  // (the next write of W.service is behind the barrier at the loop top)
+    }
+    const bool fine = n <= kFineRays && W.n_blocks > 0;
+#ifdef PT_PHASE_TIMING
+    long long pt_t0 = clock64();
+#define PT_PHASE(k)                                                                                   \
+  if (tid == 0 && p.counters) {                                                                       \
+    const long long now = clock64();                                                                  \
+    atomicAdd(p.counters + 16 + (k), (unsigned long long)(now - pt_t0));                              \
+    pt_t0 = now;                                                                                      \
+  }
+#else
+#define PT_PHASE(k)
+#endif
+    if (mode == 1 && tid == 0 && p.counters) atomicAdd(p.counters + 8, 1ull), atomicAdd(p.counters + 9, (unsigned long long)n);  // stats
+
+    // ---- BOXES (or, with media in the scene, the whole sequential scan)
+    if (sequential_scan) {
+      for (int e = tid; e < n; e += kWaveThreads) {
+        const int slot = (int)W.list_a[e];
+        const Ray ray = load_ray(slot);
+        Rng rng { W.rng[slot] };
+        const Best best = closest_hit<kSmem>(sc, sv, ray, rng, true, 0, 1);
+        W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
+        W.rng[slot] = rng.s;  // a constant_medium may have drawn from it (constant_medium.hpp:65)
+      }
+    } else {
+      // one work unit = one ray x (all its chunks | a block of kFineBoxes chunks)
+      const int n_units = fine ? n * W.n_blocks : n;
+      for (int w = tid; w < n_units; w += kWaveThreads) {
+        const int e = fine ? w / W.n_blocks : w;
+        const int slot = (int)W.list_a[e];
+        const Ray ray = load_ray(slot);
+        CullRay cr;
+        const int cull_set = make_cull_ray(sc, ray, cr);
+        const float a = vdot(ray.d, ray.d);  // sphere.hpp:69
+        Best inl { kInf, -1 };
+        unsigned long long v = kNoHit64;
+        const int4 blk = fine ? W.blocks[w - e * W.n_blocks] : make_int4(0, 0, 0, 0);
+        for (int gi = fine ? blk.x : 0; gi < (fine ? blk.x + 1 : n_groups); ++gi) {
+          const Group g = sv.groups[gi];
+          if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
+          const bool moving = g.type == G_MOVING_SPHERE;
+          const float4* boxes = moving ? sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks
+                                       : sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
+          const float f = moving ? fdiv(fsub(ray.tm, g.time0), g.den) : 0.f;
+          // the group's outsized spheres (a ground sphere ...) are tested right here, one by one: their chunks are never
+          // culled and mostly padding (the same sphere for every lane: broadcast loads)
+          // (short rounds leave them to SPHERES as items of their never-culled chunks: a shorter chain here)
+          const int open_chunks = fine ? 0 : (g.n_open + kSphereChunk - 1) / kSphereChunk;
+          if (g.n_open > 0 && !fine) {
+            const float af = filter_a(a);
+            for (int i = g.begin; i < g.begin + g.n_open; ++i) {
+              float cx, cy, cz, r2f;
+              if (moving) {
+                const float4* ps = sv.moving + moving_slot(i);
+                if ((int)sphere_filter_bits<kSmem, true>(ps, f, ray, af) < 0) {
+                  sphere_center<kSmem, true>(ps, f, cx, cy, cz, r2f);
+                  sphere_roots_scan(sc, inl, ray, a, cx, cy, cz, exact_r2(sc.moving_aux, i), make_id(G_MOVING_SPHERE, i));
+                }
+              } else {
+                const float4* ps = sv.sphere + sphere_slot(i);
+                if ((int)sphere_filter_bits<kSmem, false>(ps, f, ray, af) < 0) {
+                  sphere_center<kSmem, false>(ps, f, cx, cy, cz, r2f);
+                  sphere_roots_scan(sc, inl, ray, a, cx, cy, cz, exact_r2(sc.sphere_aux, i), make_id(G_SPHERE, i));
+                }
+              }
+            }
+          }
+          const int c_group = g.begin / kSphereChunk + open_chunks;  // the first chunk with a box
+          const int c_first = fine ? max(blk.y, c_group) : c_group;
+          const int c_end = fine ? blk.y + blk.z : (g.begin + g.count) / kSphereChunk;
+          if (inl.id >= 0) {
+            const unsigned long long w64 = pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, inl);
+            if (w64 < v) v = w64;
+            inl.t = kInf, inl.id = -1;
+          }
+          for (int cb = c_first; cb < c_end; cb += 32) {
+            emit_items(slot, ray, cr, boxes, moving, cb, min(32, c_end - cb), f, a, inl);
+            if (inl.id >= 0) {  // scanned in place: fold into the ray's winner
+              const unsigned long long w64 = pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, inl);
+              if (w64 < v) v = w64;
+              inl.t = kInf, inl.id = -1;
+            }
+          }
+        }
+        if (!fine && W.n_flats != 0) {
+          // many rays: the flat objects in front of the first medium one after the other, here (few rays: one thread per
+          // (ray, object) in SPHERES)
+          Best fb { kInf, -1 };
+          for (int gi = 0; gi < W.first_late_group; ++gi) {
+            const Group g = sv.groups[gi];
+            if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, fb);
+          }
+          if (fb.id >= 0) {
+            const unsigned long long w64 = pack_winner(fb.t, key_of(sc, fb.id));
+            if (w64 < v) v = w64;
+          }
+        }
+        if (v != kNoHit64) atomicMin(&W.best64[slot], v);
+      }
+    }
+    __syncthreads();
+    PT_PHASE(0)
+
+    // ---- SPHERES: one thread per (ray, chunk) item, or per quarter of one
+    if (!sequential_scan) {
+      const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving);
+#ifdef PT_PHASE_TIMING
+      if (tid == 0 && p.counters) atomicAdd(p.counters + 23, (unsigned long long)(n_s + n_m));
+#endif
+      if (!fine) {
+        // one index space for both kinds (a thread's items follow each other without a pass boundary in between); the
+        // moving items start at a warp boundary so that a warp runs one kind's code
+        const int m_base = (n_s + 31) & ~31;
+        for (int i = tid; i < m_base + n_m; i += kWaveThreads) {
+          if (i >= n_s && i < m_base) continue;
+          const bool moving = i >= m_base;
+          const uint2 it = W.items[moving ? kWaveItems - 1 - (i - m_base) : i];
+          const int slot = (int)(it.x & 1023u);
+          const Ray ray = load_ray(slot);
+          const float a = vdot(ray.d, ray.d);
+          Best b { kInf, -1 };
+          if (moving)
+            scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                     __uint_as_float(it.y), G_MOVING_SPHERE, b);
+          else
+            scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
+                                                      G_SPHERE, b);
+          if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
+        }
+      } else {
+        // Short rounds, ONE unit per thread where possible: a quarter of an item (its kParts threads are neighbouring lanes:
+        // lane & 15 = 4 m + q takes slots 4 m + q + 4 k, like a team of 4), or one (ray, flat object) pair for the
+        // rectangles, triangles and box sides in front of the first medium (object-major: a warp tests one object).
+        constexpr int kParts = kSphereChunk / kFineQuarter;
+        static_assert(kWaveThreads % kParts == 0 && kParts == 4, "an item's threads must be lanes 4 m .. 4 m + 3");
+        const int n_quarters = kParts * (n_s + n_m);
+        const int f_base = (n_quarters + 31) & ~31;
+        const int n_flats = W.n_flats;
+        for (int w = tid; w < f_base + n * n_flats; w += kWaveThreads) {
+          if (w < n_quarters) {
+            const int i = w / kParts;
+            const bool moving = i >= n_s;
+            const uint2 it = W.items[moving ? kWaveItems - 1 - (i - n_s) : i];
+            const int slot = (int)(it.x & 1023u);
+            const Ray ray = load_ray(slot);
+            const float a = vdot(ray.d, ray.d);
+            Best b { kInf, -1 };
+            if (moving)
+              scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                            __uint_as_float(it.y), G_MOVING_SPHERE, b);
+            else
+              scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+                                                             0.f, G_SPHERE, b);
+            if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
+          } else if (w >= f_base) {
+            const int j = (w - f_base) / n;
+            const int2 fo = W.flats[j];
+            const int slot = (int)W.list_a[(w - f_base) - j * n];
+            const Ray ray = load_ray(slot);
+            Best b { kInf, -1 };
+            if ((fo.x & 255) == G_BOX) {
+              const float4 p0 = ld4<kSmem>(sv.box + 2 * fo.y);
+              const float4 p1 = ld4<kSmem>(sv.box + 2 * fo.y + 1);
+              float t, ra, rb;
+              if (box_side_hit_t(ray, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), fo.x >> 8, kTMin, kInf, t, ra, rb))
+                b.t = t, b.id = make_id(G_BOX, fo.y);
+            } else {
+              Group g {};
+              g.type = fo.x, g.begin = fo.y, g.count = 1;
+              scan_flat_group<kSmem>(sc, sv, g, ray, fo.y, 1, b);
+            }
+            if (b.id >= 0) atomicMin(&W.best64[slot], pack_winner(b.t, key_of(sc, b.id)));
+          }
+        }
+      }
+      __syncthreads();
+    }
+    PT_PHASE(1)
+
+    // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
+    if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0;  // (SHADE builds the next round's list)
+    for (int e = tid; e < n; e += kWaveThreads) {
+      const int slot = (int)W.list_a[e];
+      Best best;
+      if (sequential_scan) {
+        best.t = W.hit_t[slot], best.id = W.hit_id[slot];
+      } else {
+        best = unpack_winner(sc, W.best64[slot]);
+        const int late = W.first_late_group;
+        if (late < n_groups) {
+          // from the first constant_medium on, in group order against the running closest hit; a medium commits
+          // unconditionally and may draw from the pixel's stream (constant_medium.hpp:52-65)
+          const Ray ray = load_ray(slot);
+          Rng rng { W.rng[slot] };
+          for (int gi = late; gi < n_groups; ++gi) {
+            const Group g = sv.groups[gi];
+            if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) {
+              scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, best);
+            } else if (g.type == G_MEDIUM) {
+              float t;
+              if (medium_hit_t(sc.media[g.begin], ray, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
+            }
+          }
+          W.rng[slot] = rng.s;
+        }
+        W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
+      }
+      W.scans[slot] += W.scans[slot] >= 0 ? 1 : -1;  // (a taken-over pixel counts downwards: -1 - rounds in the service)
+      int kind = 0;
+      if (best.id >= 0) kind = 1 + reinterpret_cast<const pt_material*>(sc.materials)[material_of(sc, best.id)].kind;
+      W.list_k[kind][atomicAdd(&W.counts[kind], 1)] = (unsigned short)slot;  // "sorted" by kind as a side effect
+      ++n_scans;
+    }
+    __syncthreads();
+    PT_PHASE(2)
+    PT_PHASE(3)
+
+    // ---- SHADE: one warp per unit of up to 32 rays of ONE kind (no divergence on the material)
+    int unit_base[kWaveKinds + 1], kind_count[kWaveKinds];  // 32-ray shading units in front of each kind
+    {
+      int units = 0;
+#pragma unroll
+      for (int k = 0; k < kWaveKinds; ++k) {
+        kind_count[k] = W.counts[k];
+        unit_base[k] = units, units += (kind_count[k] + 31) >> 5;
+      }
+      unit_base[kWaveKinds] = units;
+    }
+    const int heavy_rate = *reinterpret_cast<volatile int*>(&W.pixel_dry) ? kHeavyRateDry : kHeavyRate;
+    for (int u = warp; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
+      int kind = 0, e = 0, e_end = 0;
+#pragma unroll
+      for (int k = 0; k < kWaveKinds; ++k)
+        if (u >= unit_base[k] && u < unit_base[k + 1]) kind = k, e = ((u - unit_base[k]) << 5) + lane, e_end = kind_count[k];
+      const bool act = e < e_end;
+      const int slot = act ? (int)W.list_k[kind][e] : 0;
+      bool alive = false, own = false;
+      if (act) {
+        Ray ray = load_ray(slot);
+        const Best best { W.hit_t[slot], W.hit_id[slot] };
+        V3 att = v3(W.att_x[slot], W.att_y[slot], W.att_z[slot]);
+        V3 acc = v3(W.acc_x[slot], W.acc_y[slot], W.acc_z[slot]);
+        Rng rng { W.rng[slot] };
+        int bounce = W.bounce[slot], sample = W.sample[slot];
+        uint32_t pixq = W.pix[slot];
+        const int scans = W.scans[slot];
+        own = scans >= 0;
+        V3 contribution;
+        bool new_pixel = false;
+        alive = true;
+        if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
+          // the path ended: render.hpp:100-105
+          acc = vadd(acc, contribution);
+          int px, py;
+          float* out_px;
+          queue_pixel(p, pixq, px, py, out_px);
+          if (++sample == p.spp) {
+            if (p.order_mode == 2) {
+              p.probe_cost[pixq] = scans;  // cost probe: how deep did one sample of this pixel go
+            } else {
+              const V3 fin = vdivs(acc, fspp);
+              out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+            }
+            new_pixel = true;
+          } else {
+            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            att = v3(1.f, 1.f, 1.f);
+            bounce = 0;
+          }
+        }
+        // a heavy pixel leaves for a CTA that runs short rounds, with its complete state
+        if (!new_pixel && own && p.order_mode != 2 && scans > kHeavyBase + heavy_rate * sample &&
+            ld_volatile_u32(hq.ctrl + 1) < hq.cap) {
+          const unsigned int i = atomicAdd(hq.ctrl + 1, 1u);
+          if (i < hq.cap) {
+            float* q = hq.entries + (size_t)i * kHeavyEntryWords;
+            __stcg(q + 0, __uint_as_float(pixq)), __stcg(q + 1, __uint_as_float(rng.s));
+            __stcg(q + 2, __int_as_float(sample)), __stcg(q + 3, __int_as_float(bounce));
+            __stcg(q + 4, ray.o.x), __stcg(q + 5, ray.o.y), __stcg(q + 6, ray.o.z);
+            __stcg(q + 7, ray.d.x), __stcg(q + 8, ray.d.y), __stcg(q + 9, ray.d.z), __stcg(q + 10, ray.tm);
+            __stcg(q + 11, att.x), __stcg(q + 12, att.y), __stcg(q + 13, att.z);
+            __stcg(q + 14, acc.x), __stcg(q + 15, acc.y), __stcg(q + 16, acc.z);
+            __stcg(q + 17, __uint_as_float((uint32_t)globaltimer_ns()));
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int*>(hq.ready + i) = hq.stamp;
+            new_pixel = true;
+          }
+        }
+        if (new_pixel) {
+          if (!own && p.counters) atomicMax(p.counters + 14, (unsigned long long)(-1 - scans));  // stats: longest stay in the service
+          int px, py;
+          alive = mode == 0 && next_pixel(pixq, rng, px, py);
+          if (alive) {
+            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            att = v3(1.f, 1.f, 1.f);
+            acc = v3(0.f, 0.f, 0.f);
+            bounce = 0, sample = 0;
+            W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;
+            own = !express;
+          } else if (mode == 1) {
+            W.free_list[atomicAdd(&W.free_count, 1)] = (unsigned short)slot;  // refilled from the hand-off queue
+          }
+        }
+        if (alive) store_ray(slot, ray, att, acc, rng, bounce, sample);
+      }
+      append(alive, own, slot);
+    }
+    __syncthreads();
+    if (tid < 8) W.counts[tid] = 0;  // (everybody has read them; LATE of the next round is two barriers away)
+    PT_PHASE(4)
+#ifdef PT_PHASE_TIMING
+    if (tid == 0 && p.counters) atomicAdd(p.counters + 21, 1ull), atomicAdd(p.counters + 22, (unsigned long long)n);
+#endif
+  }
+
+  if (p.counters && lane == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
+  unsigned int warp_scans = n_scans;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) warp_scans += __shfl_xor_sync(0xffffffffu, warp_scans, o);
+  if (lane == 0 && p.counters) atomicAdd(p.counters, (unsigned long long)warp_scans);
+}
+
+// ---------------------------------------------------------------- LPT tile order
+// One block: bin the tiles by probed cost (sum of the probes inside the tile), then list them from the
+// most expensive bin to the cheapest (counting sort; the order inside a bin does not matter).
+constexpr int kCostBins = 1024;
+__global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict__ probe_cost, int region_w, int region_h,
+                                                           int tiles_x, int tiles_y, int* __restrict__ tile_order,
+                                                           int* __restrict__ tile_bin) {
+  __shared__ int hist[kCostBins];
+  __shared__ int start[kCostBins];
+  const int n_tiles = tiles_x * tiles_y;
+  const int pw = (region_w + kProbeStep - 1) / kProbeStep, ph = (region_h + kProbeStep - 1) / kProbeStep;
+  for (int b = threadIdx.x; b < kCostBins; b += blockDim.x) hist[b] = 0;
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    const int tx = t % tiles_x, ty = t / tiles_x;
+    int cost = 0;
+    for (int j = 0; j < kTile / kProbeStep; ++j)
+      for (int i = 0; i < kTile / kProbeStep; ++i) {
+        const int qx = tx * (kTile / kProbeStep) + i, qy = ty * (kTile / kProbeStep) + j;
+        if (qx < pw && qy < ph) cost += probe_cost[qy * pw + qx];
+      }
+    const int bin = min(cost, kCostBins - 1);
+    tile_bin[t] = bin;
+    atomicAdd(&hist[bin], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = kCostBins - 1; b >= 0; --b) start[b] = run, run += hist[b];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) tile_order[atomicAdd(&start[tile_bin[t]], 1)] = t;
+}
+
+cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
+                              int* tile_order, int* scratch, cudaStream_t stream) {
+  tile_order_kernel<<<1, 1024, 0, stream>>>(probe_cost, region_w, region_h, tiles_x, tiles_y, tile_order, scratch);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- launch
+int max_smem_blob_bytes(int device) {
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  return optin - 1024;
+}
+
+cudaError_t launch_render(const RenderParams& p, int device, int grid_override, cudaStream_t stream,
+                          LaunchInfo* info) {
+  int sms = 0;
+  cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (err != cudaSuccess) return err;
+  RenderParams q = p;
+  const unsigned long long pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
+  if (p.kernel_kind == 0) {
+    // ---- wavefront kernel: one CTA per SM, ray pool + (when it fits) the scan blob in shared memory
+    // shared memory: the ray pool, and in front of it the scan blob with the side tables (else the blob alone, else nothing)
+    const size_t pool_bytes = sizeof(WavePool);
+    auto with_pool = [&](size_t bytes) { return (pool_bytes + 127u) / 128u * 128u + bytes; };
+    const long long most = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc);
+    q.staged_bytes = (long long)with_pool(p.scene.stage_bytes) <= most  ? p.scene.stage_bytes
+                     : (long long)with_pool(p.scene.blob_bytes) <= most ? p.scene.blob_bytes
+                                                                        : 0u;
+    const bool smem = q.staged_bytes != 0u;
+    const size_t dyn = smem ? with_pool(q.staged_bytes) : pool_bytes;
+    auto kernel = smem ? render_wave_kernel<true> : render_wave_kernel<false>;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (err != cudaSuccess) return err;
+    // every CTA must be resident at once: the express warps wait for all CTAs to report
+    int resident = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, kWaveThreads, dyn);
+    if (err != cudaSuccess) return err;
+    if (resident < 1) return cudaErrorLaunchOutOfResources;
+    if (resident > PT_WAVE_BLOCKS_PER_SM) resident = PT_WAVE_BLOCKS_PER_SM;
+    int grid = grid_override > 0 ? grid_override : sms * resident;
+    if (grid > sms * resident) grid = sms * resident;
+    const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
+    q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
+    // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
+    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid * 23 + 100) / 200 : 0);  // 17 of 148: measured best on the default scene
+    if (q.n_express >= grid) q.n_express = grid - 1;
+    if (p.order_mode == 2) {
+      q.n_express = 0;
+      q.n_positions = (unsigned long long)((p.region.w + kProbeStep - 1) / kProbeStep) *
+                      (unsigned long long)((p.region.h + kProbeStep - 1) / kProbeStep);
+    } else if (p.order_mode == 1) {
+      q.n_positions = (unsigned long long)p.tiles_x * (unsigned long long)p.tiles_y * (unsigned long long)(kTile * kTile);
+    } else {
+      q.n_positions = pixels;
+    }
+    // with the LPT order the express CTAs start on the most expensive tiles, one pixel per pool slot
+    q.express_positions = 0;
+    if (p.order_mode == 1) {
+      q.express_positions = (unsigned long long)q.n_express * (unsigned long long)kExpressPool;
+      if (q.express_positions > q.n_positions) q.express_positions = q.n_positions;
+    }
+    {
+      const unsigned long long sh = (q.n_positions + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
+      q.pool_cap = (int)(sh < 32ull ? 32ull : (sh > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : sh));
+    }
+    // pixel-order permutation pos -> (pos * scramble) mod pixels: a multiplier near pixels / golden ratio,
+    // made coprime with the pixel count so that it is a bijection
+    unsigned long long mul = (unsigned long long)((double)pixels * 0.6180339887498949) | 1ull;
+    auto gcd = [](unsigned long long a, unsigned long long b) {
+      while (b) {
+        const unsigned long long t = a % b;
+        a = b, b = t;
+      }
+      return a;
+    };
+    while (pixels > 1 && gcd(mul % pixels, pixels) != 1ull) mul += 2ull;
+    q.scramble = pixels > 1 ? mul % pixels : 1ull;
+    if (q.scramble == 0ull) q.scramble = 1ull;
+    if (info) info->grid = grid, info->block = kWaveThreads, info->smem_bytes = (int)dyn, info->blocks_per_sm = 1, info->staged = smem, info->team_size = 0;
+    kernel<<<grid, kWaveThreads, dyn, stream>>>(q);
+    return cudaGetLastError();
+  }
+  return launch_lane(p, device, grid_override, stream, info);
+}
+
+}  // namespace ptb
