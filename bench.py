@@ -1,33 +1,36 @@
 #!/usr/bin/env python
 """bench.py -- Mpaths/s of the path-tracing hot path on B200, next to the reference's CPU path.
 
-    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
-    python bench.py --impl reference --gpus N --steps K --warmup W
+    python bench.py --gpus N --steps K --warmup W [--workload c1|c2|c3|c4|c5]   (N>1: under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W [--workload ...]
 
-A "step" is one full render of the workload: by default BASELINE config 1, the reference's default
-src/main.cpp scene at 800x480, 100 spp, depth 50 (38.4 M paths; the scene and camera come from
-tests/golden/c1_scene.ptsc.gz, captured from the unmodified main.cpp).  A path = one camera sample.
+A "step" is one full render of the workload; a path = one camera sample (one iteration of render.hpp:95-101).
+Workloads are BASELINE.json's configs; the default, c1, is the one the metric is quoted on:
 
-  value   whole-job Mpaths/s with scene and framebuffer resident in HBM (device-resident C-ABI),
-          timed with CUDA events on the launching stream, max over ranks.
-  N > 1   the path shards by pixels with no data-path collective (seeds are global linear ids), so
-          the scaling run is WEAK: every GPU renders 480 rows.  N GPUs render the default scene with
-          the SAME camera at 800 x (480 N) -- N times the rows, interleaved (row r -> rank r mod N) --
-          and the rows land in rank 0's framebuffer through peer stores over NVLink (or an NCCL
-          gather).  At N = 1 this is exactly BASELINE config 1.  (Strong scaling of the fixed
-          384 000-pixel image is capped near 2x by its deepest pixel -- 3 151 serial bounces -- see
-          DESIGN.md section 7; `--scaling strong` measures it.)
-  e2e     the same metric through the blocking host-buffer entry point (pt_render / the per-rank
-          launcher): scene upload from pinned host memory + render + framebuffer download every step.
-  roofline  FP32: achieved = value x W, W = algorithmic flop per path from the oracle's work counters
-          of this exact workload and the per-test constants of SURVEY.md appendix D;
-          peak = FFMA rate measured in this run by a register-resident micro-kernel
-          (MEASURED_PEAKS.json has no fp32 entry).  W is the work of the reference's brute-force scan; the
-          kernel skips most of it (chunk culling), so the line also carries the flops it really executes
-          (ncu counters, profiles/traffic.json) -- `achieved` is an algorithmic rate, not an issue rate.
-  cpu_baseline  the reference's CPU path (oracle/_ref/libptref.so = unmodified reference headers, or
-          the C port when that library was not built) on this box's host cores, on a bounded sample
-          of the same workload (every `stride`-th row at full spp).
+  c1  the reference's default src/main.cpp scene, 800x480, 100 spp (scene + camera captured from the unmodified
+      main.cpp: tests/golden/c1_scene.ptsc.gz)
+  c2  RTIOW random spheres, 1920x1080, 64 spp            c3  Cornell box with smoke boxes, 1024x1024, 1024 spp
+  c4  10 002-triangle pyramid mesh, 1920x1080, 256 spp   c5  4K motion blur + depth of field, 3840x2160, 4096 spp
+  (c2..c5 are built by tests/scenes.py with numpy's RandomState, not LocalPseudoRNG: "like", not identical to, the
+  scenes SURVEY.md sketches -- the oracle and the GPU get the same vectors either way.)
+
+  value   whole-job Mpaths/s with scene and framebuffer resident in HBM (device-resident C-ABI), timed with CUDA
+          events on the launching stream, max over ranks.
+  N > 1   the path shards by pixels with no data-path collective (seeds are global linear ids).  `--scaling weak`
+          (default): every GPU renders the workload's row count -- N GPUs render the same scene with the same
+          camera at height x N, rows interleaved (row r -> rank r mod N), landing in rank 0's framebuffer
+          through peer stores over NVLink (or an NCCL gather).  `--scaling strong`: the fixed image over N GPUs.
+          Every N > 1 line also carries a `strong` sub-record (the fixed image, same steps).
+  e2e     the same metric through the blocking host-buffer entry point (pt_render / the per-rank launcher):
+          scene upload from pinned host memory + render + framebuffer download every step.
+  roofline  FP32: achieved = value x W, W = algorithmic flop per path from the oracle's work counters of this
+          exact workload and the per-test constants of SURVEY.md appendix D; peak = N x the FFMA rate measured in
+          this run by a register-resident micro-kernel (MEASURED_PEAKS.json has no fp32 entry).  W is the work of
+          the reference's brute-force scan; culling skips most of it, so the line also carries the flops really
+          executed (ncu counters, profiles/traffic.json) -- `achieved` is an algorithmic rate, not an issue rate.
+  cpu_baseline  the reference's CPU path (oracle/_ref/libptref.so = unmodified reference headers where it has the
+          workload's template instantiation, else the C port) on ALL of this box's host cores, on a bounded
+          sample of the same workload at full spp.
 """
 import argparse
 import json
@@ -43,9 +46,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+
+def host_threads():
+    """The host cores this process may use (torchrun exports OMP_NUM_THREADS=1: never ask OpenMP)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# name -> description, builder, default --steps, CPU sample (a function of width, height -> pt_region + words)
+def _rows(stride):
+    def f(w, h):
+        from oracle.pyoracle import rows_region
+        return rows_region(w, h, 0, stride), "rows 0::%d of %d" % (stride, h)
+    return f
+
+
+def _tile(tw, th):
+    def f(w, h):
+        from path_tracer_b200 import abi
+        x0, y0 = (w - tw) // 2, (h - th) // 2
+        return abi.pt_region(x0, y0, tw, th, 1), "the %dx%d tile at (%d, %d)" % (tw, th, x0, y0)
+    return f
+
+
 WORKLOADS = {
-    # name: (description, fixture loader)
-    "c1": "default src/main.cpp scene, 800x480, 100 spp, depth 50 (BASELINE config 1)",
+    "c1": ("default src/main.cpp scene, 800x480, 100 spp, depth 50 (BASELINE config 1)", 10, _rows(4)),
+    "c2": ("RTIOW-like random spheres (488 spheres, numpy-RNG layout), 1920x1080, 64 spp, depth 50 (BASELINE config 2)", 10, _rows(8)),
+    "c3": ("Cornell box of thin boxes + xy_rect with two constant_medium smoke boxes and a light, 1024x1024, 1024 spp, "
+           "depth 50 (BASELINE config 3)", 3, _tile(128, 96)),
+    "c4": ("10 002-triangle pyramid mesh, checker + image textures (numpy-RNG layout), 1920x1080, 256 spp, depth 50 "
+           "(BASELINE config 4)", 3, _tile(128, 64)),
+    "c5": ("4K motion blur + depth of field, 388 moving of 485 spheres (numpy-RNG layout), 3840x2160, 4096 spp, depth 50 "
+           "(BASELINE config 5)", 1, _tile(96, 64)),
 }
 
 
@@ -54,7 +88,18 @@ def load_workload(name):
     if name == "c1":
         sc, cam, (w, h, spp, d) = scenes.load_c1()
         return sc, cam, w, h, spp, d
-    raise SystemExit("unknown workload %r" % name)
+    w, h, spp = {"c2": (1920, 1080, 64), "c3": (1024, 1024, 1024), "c4": (1920, 1080, 256), "c5": (3840, 2160, 4096)}[name]
+    build = {"c2": scenes.rtiow, "c3": scenes.cornell, "c4": scenes.c4_mesh, "c5": scenes.motion_blur}[name]
+    sc, cam = build(w / h)
+    return sc, cam, w, h, spp, 50
+
+
+def static_config(args, w, h, spp, d, world, h_total):
+    """The workload's description: identical in both arms (measured values live in `measured`)."""
+    return {"workload": WORKLOADS[args.workload][0] + ("" if world == 1 else "; %s scaling: image %dx%d over %d GPUs" % (args.scaling, w, h_total, world)),
+            "width": w, "height": h_total, "spp": spp, "depth": d, "paths_per_step": w * h_total * spp,
+            "partition": "rows interleaved over %d rank(s)" % world, "gather": args.gather if world > 1 else "none",
+            "l2": "256 MiB memset between timed iterations"}
 
 
 # ---- algorithmic work per path (SURVEY.md appendix D, "hoisted minimum" column) ------------------
@@ -123,16 +168,6 @@ class ClockSampler:
 
 
 # ---- the reference arm / cpu baseline ---------------------------------------------------------------
-def cpu_sample(oracle, sc, cam, w, h, spp, d, stride, dynamic):
-    from oracle.pyoracle import rows_region
-    region = rows_region(w, h, 0, stride)
-    t0 = time.perf_counter()
-    res = oracle.render_region(sc, cam, w, h, spp, d, region, dynamic=dynamic, nthreads=0)
-    dt = time.perf_counter() - t0
-    paths = region.w * region.h * spp
-    return paths / dt / 1e6, dt, paths, res
-
-
 def pick_cpu_oracle(w, h, spp, d):
     from oracle.pyoracle import CPort, Ref
     if Ref.available():
@@ -142,34 +177,74 @@ def pick_cpu_oracle(w, h, spp, d):
     return CPort()
 
 
+def cpu_sample(oracle, sc, cam, w, h, spp, d, region, dynamic):
+    """Render `region` at full spp on all host cores.  -> (Mpaths/s, seconds, paths, counters or None)"""
+    t0 = time.perf_counter()
+    res = oracle.render_region(sc, cam, w, h, spp, d, region, dynamic=dynamic, nthreads=host_threads())
+    dt = time.perf_counter() - t0
+    paths = region.w * region.h * spp
+    counters = res[1].as_dict() if isinstance(res, tuple) else None
+    return paths / dt / 1e6, dt, paths, counters
+
+
+def cpu_baseline_record(args, sc, cam, w, h, spp, d, with_dynamic=True):
+    """-> (record, oracle counters of the sample or None)"""
+    oracle = pick_cpu_oracle(w, h, spp, d)
+    region, words = WORKLOADS[args.workload][2](w, h)
+    if args.workload == "c1" and args.cpu_stride:
+        region, words = _rows(args.cpu_stride)(w, h)
+    v_static, dt, paths, counters = cpu_sample(oracle, sc, cam, w, h, spp, d, region, False)
+    rec = {"value": v_static, "unit": "Mpaths/s", "cores": host_threads(), "kind": oracle.kind,
+           "sample": "%s at full spp (%d paths), OpenMP schedule(static) over rows like triSYCL's host parallel_for; %.1f s"
+                     % (words, paths, dt)}
+    if with_dynamic:
+        v_dyn, dt2, _, _ = cpu_sample(oracle, sc, cam, w, h, spp, d, region, True)
+        rec["value_dynamic_schedule"] = v_dyn
+        rec["sample"] += " + %.1f s (dynamic)" % dt2
+    return rec, counters
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on this box's host cores, same config / metric / unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = args.gpus
     sc, cam, w, h, spp, d = load_workload(args.workload)
-    # the reference's CPU path has one configuration (one box, its host cores): BASELINE config 1
+    h_total = h * world if args.scaling == "weak" else h
     oracle = pick_cpu_oracle(w, h, spp, d)
-    stride = args.cpu_stride
+    region, words = WORKLOADS[args.workload][2](w, h)
+    if args.workload == "c1" and args.cpu_stride:
+        region, words = _rows(args.cpu_stride)(w, h)
+    from path_tracer_b200 import abi
+    small = abi.pt_region(region.x0, region.y0, region.w, max(region.h // 4, 1), region.y_stride)
     for _ in range(args.warmup):
-        cpu_sample(oracle, sc, cam, w, h, spp, d, stride * 4, False)
-    t_total, paths_total = 0.0, 0
-    for _ in range(args.steps):
-        _, dt, paths, _ = cpu_sample(oracle, sc, cam, w, h, spp, d, stride, False)
+        cpu_sample(oracle, sc, cam, w, h, spp, d, small, False)
+    t_total, paths_total, full_step = 0.0, 0, None
+    for it in range(args.steps):
+        if it == 0 and oracle.kind == "reference" and hasattr(oracle, "render_full") and d == 50:
+            # the first timed step goes through the reference's OWN entry point, render<W,H,S>() (render.hpp:141-160),
+            # on the whole frame; the others through render_pixel<> on the bounded sample
+            t0 = time.perf_counter()
+            oracle.render_full(sc, cam, w, h, spp, dynamic=False, nthreads=host_threads())
+            dt, paths = time.perf_counter() - t0, w * h * spp
+            full_step = {"entry": "render<%d,%d,%d>()" % (w, h, spp), "seconds": dt, "Mpaths/s": paths / dt / 1e6}
+        else:
+            _, dt, paths, _ = cpu_sample(oracle, sc, cam, w, h, spp, d, region, False)
         t_total += dt
         paths_total += paths
     value = paths_total / t_total / 1e6
-    dyn, _, _, _ = cpu_sample(oracle, sc, cam, w, h, spp, d, stride, True)
-    cores = oracle.max_threads()
     line = {
         "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "reference default scene (fixture captured from the unmodified main.cpp); no external data",
-        "config": {"workload": WORKLOADS[args.workload], "width": w, "height": h, "spp": spp, "depth": d},
-        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": cores, "kind": oracle.kind,
-                         "sample": "rows 0::%d of %d at full spp (%d paths/step), OpenMP schedule(static) over rows "
-                                   "like triSYCL's host parallel_for" % (stride, h, paths_total // args.steps),
-                         "value_dynamic_schedule": dyn},
+        "data": "synthetic (reference default scene captured from the unmodified main.cpp / procedural scenes); no external data",
+        "config": static_config(args, w, h, spp, d, world, h_total),
+        "cpu_baseline": {"value": value, "unit": "Mpaths/s", "cores": host_threads(), "kind": oracle.kind,
+                         "sample": "%s at full spp per step%s, OpenMP schedule(static) over rows like triSYCL's host "
+                                   "parallel_for; the CPU path has one configuration (one box, its host cores): the "
+                                   "workload's base image" % (words, ", the first step the whole frame" if full_step else ""),
+                         "full_frame_step": full_step},
         "e2e": {"value": value, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -180,16 +255,19 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c1", choices=sorted(WORKLOADS))
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"])
-    ap.add_argument("--cpu-stride", type=int, default=4, help="cpu baseline renders rows 0::stride")
+    ap.add_argument("--cpu-stride", type=int, default=0, help="c1: the cpu baseline renders rows 0::stride (default 4)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = 480 rows per GPU (image 800 x 480N), strong = the fixed 800x480 image")
+                    help="N > 1: weak = the workload's rows per GPU (image height x N), strong = the fixed image")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the fixed-image `strong` sub-record")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = WORKLOADS[args.workload][1]
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -214,58 +292,66 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    sc, cam, w, h, spp, d = load_workload(args.workload)
-    if args.scaling == "weak":
-        h = h * world  # same scene and camera, N times the rows: every rank renders the base image's row count
-    paths_per_step = w * h * spp
+    sc, cam, w, h_base, spp, d = load_workload(args.workload)
+    h = h_base * world if args.scaling == "weak" else h_base  # weak: same scene and camera, N times the rows
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident: `value`
-    rend = ptdist.DistRenderer(sc, cam, w, h, spp, d, rank, world, local_rank, mode=args.gather)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
-    for _ in range(args.warmup):
-        rend.launch()
-        rend.gather()
-    rend.scene.counters(reset=True)
-    launches0 = rend.scene.launch_count()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()                       # L2 flush between timed iterations (not inside the event pair)
-        a.record(stream)
-        rend.launch()
-        if args.gather == "nccl" and world > 1:
+
+    def timed_run(height, steps, sample_clocks):
+        """Device-resident renders of the image w x height over the ranks -> dict (timing max over ranks)."""
+        rend = ptdist.DistRenderer(sc, cam, w, height, spp, d, rank, world, local_rank, mode=args.gather)
+        for _ in range(args.warmup):
+            rend.launch()
             rend.gather()
-        b.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    paths_done, scans_done = rend.scene.counters()
-    launches = rend.scene.launch_count() - launches0
-    t = torch.tensor([dev_ms, float(scans_done), float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, scans_total, launches = float(tmax[0]), float(tsum[1]), int(tsum[2])
-    else:
-        scans_total = float(scans_done)
-    ms_per_step = dev_ms / args.steps
-    value = paths_per_step / (ms_per_step * 1e-3) / 1e6
-    final = rend.gather()
-    fb_check = float(final.mean()) if rank == 0 else None
+        rend.scene.counters(reset=True)
+        launches0 = rend.scene.launch_count()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()                       # L2 flush between timed iterations (not inside the event pair)
+            a.record(stream)
+            rend.launch()
+            if args.gather == "nccl" and world > 1:
+                rend.gather()
+            b.record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop() if rank == 0 and sample_clocks else None
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        _, scans_done = rend.scene.counters()
+        launches = rend.scene.launch_count() - launches0
+        t = torch.tensor([dev_ms, float(scans_done), float(launches)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dev_ms, scans_total, launches = float(tmax[0]), float(tsum[1]), int(tsum[2])
+        else:
+            scans_total = float(scans_done)
+        ms_per_step = dev_ms / steps
+        paths = w * height * spp
+        final = rend.gather()
+        return {"rend": rend, "ms_per_step": ms_per_step, "value": paths / (ms_per_step * 1e-3) / 1e6, "paths": paths,
+                "scans_per_path": scans_total / (paths * steps), "launches": launches // max(steps, 1), "clocks": clocks,
+                "fb_mean": float(final.mean()) if rank == 0 else None, "wall_ms": 1e3 * t_wall / steps}
+
+    # ---------------- device-resident: `value`
+    run = timed_run(h, args.steps, True)
+    rend = run["rend"]
+    paths_per_step = run["paths"]
+    value, ms_per_step = run["value"], run["ms_per_step"]
 
     # ---------------- end to end through the host-buffer API: `e2e`
     fb_host = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
@@ -273,7 +359,9 @@ def main():
     sc.texture_bytes = pinned_tex.numpy()
     h2d = d2h = 0
     e2e_times = []
-    for it in range(args.warmup + args.steps):
+    e2e_steps = args.steps if ms_per_step < 2000 else 1  # (a 20 s frame is not repeated ten times over)
+    e2e_warm = args.warmup if ms_per_step < 2000 else 0
+    for it in range(e2e_warm + e2e_steps):
         barrier()
         t0 = time.perf_counter()
         if world == 1:
@@ -293,77 +381,103 @@ def main():
             d2h = h * w * 12
             scene2.close()
         barrier()
-        if it >= args.warmup:
+        if it >= e2e_warm:
             e2e_times.append(time.perf_counter() - t0)
     e2e_t = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = paths_per_step * args.steps / float(e2e_t[0]) / 1e6
+    e2e_value = paths_per_step * e2e_steps / float(e2e_t[0]) / 1e6
     e2e_mean = float(fb_host.mean())
+    rend.close()
+
+    # ---------------- N > 1: the fixed image over N GPUs (strong scaling), and the single-process multi-GPU entry
+    strong = single = None
+    if world > 1 and not args.no_strong:
+        if args.scaling == "weak":
+            s_run = timed_run(h_base, args.steps, False)
+            s_run["rend"].close()
+            strong = {"value": s_run["value"], "unit": "Mpaths/s", "ms_per_step": s_run["ms_per_step"],
+                      "image": "%dx%d" % (w, h_base), "paths_per_step": s_run["paths"],
+                      "note": "the workload's fixed image, rows interleaved over %d GPUs; compare with the N = 1 line" % world}
+        barrier()
+        if rank == 0 and R.device_count() >= 2:
+            # pt_set_num_gpus(2) -> pt_render: one process driving two GPUs, peer stores into GPU 0's framebuffer
+            sspp = max(spp // 25, 1)
+            one = R.render(sc, cam, w, h_base, sspp, d)
+            R.set_num_gpus(2)
+            try:
+                t0 = time.perf_counter()
+                two = R.render(sc, cam, w, h_base, sspp, d)
+                dt = time.perf_counter() - t0
+            finally:
+                R.set_num_gpus(1)
+            single = {"n_gpus": 2, "spp": sspp, "bit_identical_to_one_gpu": bool(np.array_equal(one.view(np.uint32), two.view(np.uint32))),
+                      "seconds_incl_upload": dt}
+        barrier()
 
     if rank != 0:
-        rend.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---------------- rank 0: roofline + cpu baseline + the JSON line
     peak_tflops, peak_mhz = R.measure_fp32_peak(local_rank)
-    cpu = None
-    counters = None
-    if world == 1 and not args.no_cpu_baseline:
-        oracle = pick_cpu_oracle(w, h, spp, d)
-        v_static, dt, paths, _ = cpu_sample(oracle, sc, cam, w, h, spp, d, args.cpu_stride, False)
-        v_dyn, dt2, _, _ = cpu_sample(oracle, sc, cam, w, h, spp, d, args.cpu_stride, True)
-        cpu = {"value": v_static, "unit": "Mpaths/s", "cores": oracle.max_threads(), "kind": oracle.kind,
-               "sample": "rows 0::%d of %d at full spp (%d paths), OpenMP schedule(static) over rows like triSYCL's "
-                         "host parallel_for; %.1f s + %.1f s (dynamic)" % (args.cpu_stride, h, paths, dt, dt2),
-               "value_dynamic_schedule": v_dyn}
-    # work counters for W: the C port counts them; a 1-in-16 row sample at full spp is plenty
-    try:
-        from oracle.pyoracle import CPort, rows_region
-        _, cnt = CPort().render_region(sc, cam, w, h, spp, d, rows_region(w, h, 0, 16 * world))
-        counters = cnt.as_dict()
-        flop_per_path = flops_per_path(counters)
-    except OSError:
-        flop_per_path = 26.4e3  # SURVEY.md section 8(d), default scene
+    cpu = counters = None
+    if not args.no_cpu_baseline:
+        cpu, counters = cpu_baseline_record(args, sc, cam, w, h_base, spp, d)
+    if counters is None:
+        # work counters for W: the C port counts them; a small sample at full spp is plenty
+        try:
+            from oracle.pyoracle import CPort, rows_region
+            from path_tracer_b200 import abi
+            if args.workload in ("c1", "c2"):
+                reg = rows_region(w, h_base, 0, 16 if args.workload == "c1" else 60)
+            else:
+                big, _ = WORKLOADS[args.workload][2](w, h_base)
+                reg = abi.pt_region(big.x0, big.y0, max(big.w // 4, 1), max(big.h // 4, 1), 1)
+            _, cnt = CPort().render_region(sc, cam, w, h_base, spp, d, reg, nthreads=host_threads())
+            counters = cnt.as_dict()
+        except OSError:
+            counters = None
+    flop_per_path = flops_per_path(counters) if counters else float("nan")
     achieved = value * 1e6 * flop_per_path / 1e12
     traffic = executed = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         prof = json.load(open(tpath))
         traffic = prof.get(args.workload)
-        if prof.get(args.workload + "_executed_flop_per_launch") and world == 1:
-            executed = prof[args.workload + "_executed_flop_per_launch"] / paths_per_step
+        if prof.get(args.workload + "_executed_flop_per_launch"):
+            executed = prof[args.workload + "_executed_flop_per_launch"] / prof.get(args.workload + "_paths_per_launch", w * h_base * spp)
+    peak_total = peak_tflops * world
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32",
-        "data": "reference default scene (fixture captured from the unmodified main.cpp); no external data",
-        "config": {"workload": WORKLOADS[args.workload] + ("" if world == 1 else
-                                                             "; %s scaling: image 800x%d over %d GPUs" % (args.scaling, h, world)),
-                   "width": w, "height": h, "spp": spp, "depth": d,
-                   "paths_per_step": paths_per_step, "partition": "rows interleaved over %d rank(s)" % world,
-                   "gather": args.gather if world > 1 else "none", "l2": "256 MiB memset between timed iterations",
-                   "scans_per_path": scans_total / (paths_per_step * args.steps), "fb_mean": fb_check,
-                   "e2e_fb_mean": e2e_mean, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
-        "clocks": clocks,
+        "data": "synthetic (reference default scene captured from the unmodified main.cpp / procedural scenes); no external data",
+        "config": static_config(args, w, h_base, spp, d, world, h),
+        "measured": {"scans_per_path": run["scans_per_path"], "fb_mean": run["fb_mean"], "e2e_fb_mean": e2e_mean,
+                     "wall_ms_per_step_incl_flush": run["wall_ms"], "e2e_steps": e2e_steps},
+        "clocks": run["clocks"],
         "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * float(e2e_t[0]) / args.steps},
-        "gpu_launches": int(launches),  # per step: cost probe + tile sort + render kernel, on every rank
-        "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tflops, "traffic": traffic, "flop_per_path": flop_per_path,
-                     # what the kernel really executes (ncu, profiles/traffic.json): chunk culling skips most of the
-                     # reference's brute-force sphere tests, so `achieved` (ALGORITHMIC flops / time) is not an issue rate
+                "ms_per_step": 1e3 * float(e2e_t[0]) / e2e_steps},
+        "gpu_launches": int(run["launches"]),  # per step, all ranks: cost probe + tile sort + render kernel on each
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_total, "unit": "TFLOP/s",
+                     "frac": achieved / peak_total, "traffic": traffic, "flop_per_path": flop_per_path,
+                     "peak_per_gpu": peak_tflops, "n_gpus": world,
+                     # what the kernel really executes (ncu, profiles/traffic.json): culling skips most of the
+                     # reference's brute-force tests, so `achieved` (ALGORITHMIC flops / time) is not an issue rate
                      "executed_flop_per_path": executed,
                      "executed_tflops": None if executed is None else value * 1e6 * executed / 1e12,
-                     "peak_source": "FFMA micro-kernel measured in this run (%.0f MHz implied); MEASURED_PEAKS.json "
-                                    "has no fp32 entry; `achieved` counts the reference's brute-force scan (every object "
-                                    "for every ray), of which the kernel executes about one sixth" % peak_mhz},
+                     "peak_source": "%d x the FFMA micro-kernel rate measured in this run (%.0f MHz implied); "
+                                    "MEASURED_PEAKS.json has no fp32 entry; `achieved` counts the reference's brute-force "
+                                    "scan (every object for every ray), most of which culling skips" % (world, peak_mhz)},
         "cpu_baseline": cpu,
     }
+    if strong is not None:
+        line["strong"] = strong
+    if single is not None:
+        line["single_process_multi_gpu"] = single
     print(json.dumps(line))
-    rend.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

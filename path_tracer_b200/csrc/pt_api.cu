@@ -47,7 +47,8 @@ int cuda_fail(cudaError_t e, const char* what) {
   } while (0)
 
 constexpr int kCounterSlots = 64;
-constexpr unsigned kHeavyCap = 32768;  // entries of the heavy-pixel hand-off queue
+constexpr unsigned kHeavyCap = 32768;  // slots of the heavy-pixel hand-off ring (a power of two)
+static_assert((kHeavyCap & (kHeavyCap - 1)) == 0, "the ring indexes with pos & (cap - 1)");
 constexpr int kCounterWords = 24;  // [0] scans, [1] first CTA start (ns), [2] queue ran dry (ns), [3] last warp retired (ns)
 
 }  // namespace
@@ -119,12 +120,17 @@ void cached_free(int device, void* ptr, size_t bytes) {
     g_cache.push_back(CachedBlock { device, ptr, bytes });
     if (g_cache.size() > kCacheEntries) {
       evict = g_cache.front().ptr;
-      const int d = g_cache.front().device;
+      device = g_cache.front().device;
       g_cache.erase(g_cache.begin());
-      cudaSetDevice(d);
     }
   }
-  if (evict) cudaFree(evict);
+  if (evict) {  // free on the block's own device, and leave the caller's current device as it was
+    int current = 0;
+    cudaGetDevice(&current);
+    cudaSetDevice(device);
+    cudaFree(evict);
+    cudaSetDevice(current);
+  }
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -214,7 +220,9 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
     e = cudaMemcpyAsync(ds->arena + o_bytes, scene->texture_bytes, scene->n_texture_bytes, cudaMemcpyHostToDevice, 0);
   else if (e == cudaSuccess)
     e = cudaMemsetAsync(ds->arena + o_bytes, 0, 3, 0);
-  if (e == cudaSuccess) e = cudaMemsetAsync(ds->arena + o_hready, 0, sizeof(unsigned) * kHeavyCap, 0);
+  std::vector<unsigned> ring_init(kHeavyCap);  // slot i is ready to be written for position i
+  for (unsigned i = 0; i < kHeavyCap; ++i) ring_init[i] = i;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ds->arena + o_hready, ring_init.data(), sizeof(unsigned) * kHeavyCap, cudaMemcpyHostToDevice, 0);
   cudaEventRecord(ev1, 0);
   if (e == cudaSuccess) e = cudaEventSynchronize(ev1);
   float ms = 0.f;
@@ -235,6 +243,8 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   d.n_groups = ps.n_groups;
   d.off_groups = ps.off_groups, d.off_sphere = ps.off_sphere, d.off_moving = ps.off_moving;
   d.off_rect = ps.off_rect, d.off_triangle = ps.off_triangle, d.off_box = ps.off_box;
+  d.off_trees = ps.off_trees, d.off_nodes = ps.off_nodes, d.off_tree_ids = ps.off_tree_ids, d.n_trees = ps.n_trees;
+  d.flat_extent = ps.flat_extent;
   d.n_objects = ps.n_objects;
   d.sphere_aux = reinterpret_cast<const SphereAux*>(ds->arena + o_saux);
   d.moving_aux = reinterpret_cast<const SphereAux*>(ds->arena + o_maux);
@@ -370,6 +380,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   }
   RenderParams p;
   p.scene = scene->desc;
+  p.scene.flat_cull = g_cull_enabled ? 1u : 0u;
   p.cam = *camera;
   p.width = width, p.height = height, p.spp = spp, p.depth = depth;
   p.region = *region;
@@ -393,7 +404,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   PT_CUDA(cudaMemsetAsync(p.counters + 1, 0xff, 2 * sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 3, 0, 2 * sizeof(unsigned long long), st));
   PT_CUDA(cudaMemsetAsync(p.counters + 5, 0xff, sizeof(unsigned long long), st));
-  PT_CUDA(cudaMemsetAsync(p.counters + 6, 0, sizeof(unsigned long long), st));
+  PT_CUDA(cudaMemsetAsync(p.counters + 6, 0, 2 * sizeof(unsigned long long), st));  // [6] last CTA out, [7] pixels handed off
   PT_CUDA(cudaMemsetAsync(p.counters + 8, 0, 16 * sizeof(unsigned long long), st));  // hand-off service statistics
 
   // Longest-processing-time-first pixel order (wavefront kernel, images worth it): a cost probe traces
@@ -421,7 +432,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
     probe.kernel_kind = 0;  // the probe always runs on the wavefront kernel
     probe.pixel_counter = next_queue_head();
     probe.heavy.stamp = ++scene->launch_stamp;
-    PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
+    PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl + 2, 0, sizeof(unsigned), st));
     PT_CUDA(cudaMemsetAsync(probe.pixel_counter, 0, 2 * sizeof(unsigned long long), st));
     cudaError_t pe = launch_render(probe, scene->device, 0, st, nullptr);
     if (pe != cudaSuccess) return cuda_fail(pe, "cost probe launch");
@@ -432,7 +443,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   }
   p.pixel_counter = next_queue_head();
   p.heavy.stamp = ++scene->launch_stamp;
-  PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl, 0, 64, st));
+  PT_CUDA(cudaMemsetAsync(scene->heavy_ctrl + 2, 0, sizeof(unsigned), st));
   PT_CUDA(cudaMemsetAsync(p.pixel_counter, 0, 2 * sizeof(unsigned long long), st));
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
@@ -529,7 +540,7 @@ int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[11]) {
   PT_CUDA(cudaMemcpy(ctrl, scene->heavy_ctrl, sizeof ctrl, cudaMemcpyDeviceToHost));
   out[0] = v[2] - v[1], out[1] = v[3] - v[1];
   out[2] = v[5] - v[1], out[3] = v[6] - v[1];  // first / last CTA out of regular work
-  out[4] = ctrl[1];                            // heavy pixels handed to the express lane
+  out[4] = v[7];                               // heavy pixels handed to the express lane
   out[5] = v[8], out[6] = v[9], out[7] = v[12], out[8] = v[13], out[9] = v[14], out[10] = v[15];
   if (const char* env = std::getenv("PT_PHASE_TIMING")) {  // debug builds (-DPT_PHASE_TIMING): cycles per phase
     (void)env;
@@ -595,9 +606,9 @@ int pt_render_region(int width, int height, int spp, int depth, const pt_camera*
     st.d2h_bytes = row_floats * region->h * sizeof(float);
     st.kernel_launches = ds->kernel_launches;
     uint64_t paths = 0, scans = 0;
-    pt_scene_read_counters(ds, &paths, &scans, 0);
+    rc = pt_scene_read_counters(ds, &paths, &scans, 0);  // (also where a device-side error flag becomes an error code)
     st.paths = (uint64_t)region->w * region->h * spp, st.scans = scans;
-    g_stats = st;
+    if (rc == PT_OK) g_stats = st;
   }
   for (auto& x : ev) cudaEventDestroy(x);
   cudaStreamSynchronize(0);
@@ -624,16 +635,20 @@ int pt_render(int width, int height, int spp, int depth, const pt_camera* camera
   std::vector<pt_device_scene*> scenes(n, nullptr);
   std::vector<float*> local(n, nullptr);
   std::vector<cudaStream_t> streams(n, nullptr);
-  std::vector<cudaEvent_t> ev0(n), ev1(n);
+  std::vector<cudaEvent_t> ev0(n, nullptr), ev1(n, nullptr);
+  std::vector<char> peer_enabled(n, 0);
   float* fb0 = nullptr;
   int rc = PT_OK;
   const size_t row_floats = (size_t)width * 3;
   auto cleanup = [&]() {
     for (int d = 0; d < n; ++d) {
       cudaSetDevice(d);
+      if (ev0[d]) cudaEventDestroy(ev0[d]);
+      if (ev1[d]) cudaEventDestroy(ev1[d]);
       if (local[d]) cudaFree(local[d]);
       if (streams[d]) cudaStreamDestroy(streams[d]);
       if (scenes[d]) pt_scene_free(scenes[d]);
+      if (peer_enabled[d]) cudaDeviceDisablePeerAccess(0);  // (only what this call enabled)
     }
     cudaSetDevice(0);
     if (fb0) cudaFree(fb0);
@@ -658,6 +673,7 @@ int pt_render(int width, int height, int spp, int depth, const pt_camera* camera
       cudaDeviceCanAccessPeer(&can, d, 0);
       if (can) {
         e = cudaDeviceEnablePeerAccess(0, 0);
+        if (e == cudaSuccess) peer_enabled[d] = 1;
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
         cudaGetLastError();
       }
@@ -684,8 +700,8 @@ int pt_render(int width, int height, int spp, int depth, const pt_camera* camera
     float ms = 0.f;
     if (rc == PT_OK && cudaEventElapsedTime(&ms, ev0[d], ev1[d]) == cudaSuccess) st.kernel_ms = std::max<double>(st.kernel_ms, ms);
     uint64_t scans = 0;
-    if (rc == PT_OK && pt_scene_read_counters(scenes[d], nullptr, &scans, 0) == PT_OK) st.scans += scans;
-    cudaEventDestroy(ev0[d]), cudaEventDestroy(ev1[d]);
+    if (rc == PT_OK) rc = pt_scene_read_counters(scenes[d], nullptr, &scans, 0);
+    st.scans += scans;
   }
   if (rc == PT_OK) {
     cudaSetDevice(0);

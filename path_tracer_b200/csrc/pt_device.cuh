@@ -13,8 +13,13 @@
 #ifndef PT_DEVICE_CUH
 #define PT_DEVICE_CUH
 
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#define PT_STAT(counter)
+#else
+#include "pt_hostshim.h"  // tests/host: a CPU build of these headers, for the scan-equivalence tests only
+#endif
 #include <stdint.h>
 
 namespace ptb {

@@ -19,16 +19,18 @@ constexpr int kBlockThreads = PT_BLOCK_THREADS;
 constexpr int kMinBlocksPerSM = PT_MIN_BLOCKS_PER_SM;
 constexpr int kMaxBlocksPerSM = PT_MIN_BLOCKS_PER_SM;  // persistent grid = SMs x this
 
-// Global hand-off queue for HEAVY pixels (wavefront kernel): bounded, written once per entry per
-// launch, consumed by the express CTAs and by every CTA whose own pixels have run out.  ctrl[0] = head,
-// ctrl[1] = tail, ctrl[2] = CTAs whose regular work is finished (they hand nothing off any more).
+// Global hand-off queue for HEAVY pixels (wavefront kernel): a bounded multi-producer / multi-consumer ring,
+// filled by CTAs whose pixels turn out to be deep, drained by the express CTAs and by every CTA whose own pixels
+// have run out.  ctrl[0] = head and ctrl[1] = tail are free-running positions that live on across launches (a
+// launch leaves the ring empty and every slot ready for its next lap); ctrl[2] = CTAs whose regular work is
+// finished (they hand nothing off any more), reset per launch.
 constexpr int kHeavyEntryWords = 20;
 struct HeavyQueue {
   unsigned int* ctrl;
-  unsigned int* ready;   // ready[i] == stamp once entry i is fully written
+  unsigned int* ready;   // per slot: the position the slot is ready for (pos: write, pos + 1: read); starts at the slot's index
   float* entries;        // kHeavyEntryWords words per entry
-  unsigned int cap;
-  unsigned int stamp;    // changes every launch, so `ready` never needs clearing
+  unsigned int cap;      // slots, a power of two
+  unsigned int stamp;    // (launch number; informational)
 };
 
 struct RenderParams {

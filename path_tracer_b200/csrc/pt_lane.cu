@@ -164,15 +164,7 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
     mbar_wait(&stage_bar, 0);
     blob_base = smem_blob;
   }
-  SceneView sv;
-  sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
-  sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
-  sv.moving = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
-  sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
-  sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
-  sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
-  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
-  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
+  const SceneView sv = scene_view(sc, blob_base);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   unsigned int n_scans = 0;

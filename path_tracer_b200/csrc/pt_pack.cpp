@@ -13,6 +13,7 @@
 #include "pt_pack.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -72,9 +73,139 @@ void kd_order(std::vector<RawSphere>& v, size_t lo, size_t hi) {
   kd_order(v, mid, hi);
 }
 
+
+// ---------------------------------------------------------------- flat groups: k-d order, box trees, grazing index
+struct DBox {  // bounding box in binary64; `open` = not finite: never culled
+  double lo[3], hi[3];
+  bool open;
+};
+DBox box_of_points(const double (*p)[3], int n) {
+  DBox b;
+  b.open = false;
+  for (int k = 0; k < 3; ++k) {
+    b.lo[k] = std::numeric_limits<double>::infinity(), b.hi[k] = -b.lo[k];
+    for (int i = 0; i < n; ++i) {
+      if (!std::isfinite(p[i][k])) b.open = true;
+      b.lo[k] = std::min(b.lo[k], p[i][k]), b.hi[k] = std::max(b.hi[k], p[i][k]);
+    }
+  }
+  return b;
+}
+void grow(DBox& a, const DBox& b) {
+  a.open = a.open || b.open;
+  for (int k = 0; k < 3; ++k) a.lo[k] = std::min(a.lo[k], b.lo[k]), a.hi[k] = std::max(a.hi[k], b.hi[k]);
+}
+float round_down(double x) {
+  float f = (float)x;
+  if ((double)f > x) f = std::nextafter(f, -std::numeric_limits<float>::infinity());
+  return f;
+}
+float round_up(double x) {
+  float f = (float)x;
+  if ((double)f < x) f = std::nextafter(f, std::numeric_limits<float>::infinity());
+  return f;
+}
+
+// k-d order of perm[lo, hi) by the points `pts`: median splits along the widest axis, at multiples of the largest
+// leaf * kTreeFan^k below the range's size, so that EVERY aligned run of leaf * kTreeFan^k elements (= a tree
+// node) is a union of k-d cells, i.e. spatially compact.
+void kd_order_aligned(std::vector<int>& perm, const std::vector<std::array<double, 3>>& pts, size_t lo, size_t hi, size_t leaf) {
+  const size_t n = hi - lo;
+  if (n <= leaf) return;
+  size_t block = leaf;
+  while (block * (size_t)kTreeFan < n) block *= (size_t)kTreeFan;
+  int axis = 0;
+  double widest = -1;
+  for (int k = 0; k < 3; ++k) {
+    double mn = std::numeric_limits<double>::infinity(), mx = -mn;
+    for (size_t i = lo; i < hi; ++i) mn = std::min(mn, pts[(size_t)perm[i]][(size_t)k]), mx = std::max(mx, pts[(size_t)perm[i]][(size_t)k]);
+    if (mx - mn > widest) widest = mx - mn, axis = k;
+  }
+  size_t k = (n / 2 + block / 2) / block;
+  if (k < 1) k = 1;
+  if (k * block >= n) k = (n - 1) / block;
+  const size_t mid = lo + k * block;
+  std::nth_element(perm.begin() + (long)lo, perm.begin() + (long)mid, perm.begin() + (long)hi,
+                   [&pts, axis](int a, int b) { return pts[(size_t)a][(size_t)axis] < pts[(size_t)b][(size_t)axis]; });
+  kd_order_aligned(perm, pts, lo, mid, leaf);
+  kd_order_aligned(perm, pts, mid, hi, leaf);
+}
+
+// Box tree over elements that are already in their final order: leaves of `leaf` consecutive elements, kTreeFan
+// children per inner node, boxes rounded outward to binary32 ({lo} {hi} float4 pairs appended to `nodes`).
+Tree build_tree(const std::vector<DBox>& elem, size_t leaf, std::vector<f4>& nodes, double* extent) {
+  Tree t {};
+  t.leaf_ids = -1;
+  std::vector<DBox> level;
+  for (size_t i = 0; i < elem.size(); i += leaf) {
+    DBox b = elem[i];
+    for (size_t j = i + 1; j < std::min(elem.size(), i + leaf); ++j) grow(b, elem[j]);
+    level.push_back(b);
+  }
+  const float inf = std::numeric_limits<float>::infinity();
+  for (int l = 0; l < kTreeLevels; ++l) {
+    t.off[l] = (int32_t)nodes.size(), t.n[l] = (int32_t)level.size(), t.levels = l + 1;
+    for (const DBox& b : level) {
+      if (b.open) {
+        nodes.push_back(f4 { -inf, -inf, -inf, 0.f }), nodes.push_back(f4 { inf, inf, inf, 0.f });
+      } else {
+        nodes.push_back(f4 { round_down(b.lo[0]), round_down(b.lo[1]), round_down(b.lo[2]), 0.f });
+        nodes.push_back(f4 { round_up(b.hi[0]), round_up(b.hi[1]), round_up(b.hi[2]), 0.f });
+        if (extent)
+          for (int k = 0; k < 3; ++k) *extent = std::max(*extent, std::max(std::fabs(b.lo[k]), std::fabs(b.hi[k])));
+      }
+    }
+    if (level.size() <= 32 || l + 1 == kTreeLevels) break;
+    std::vector<DBox> up;
+    for (size_t i = 0; i < level.size(); i += (size_t)kTreeFan) {
+      DBox b = level[i];
+      for (size_t j = i + 1; j < std::min(level.size(), i + (size_t)kTreeFan); ++j) grow(b, level[j]);
+      up.push_back(b);
+    }
+    level.swap(up);
+  }
+  return t;
+}
+
+// Reorder the `per` float4 per element of `data` (and the matching aux entries) by `perm`.
+template <typename Aux> void permute_flat(std::vector<f4>& data, std::vector<Aux>& aux, const std::vector<int>& perm, int per) {
+  std::vector<f4> d2(data.size());
+  std::vector<Aux> a2(aux.size());
+  for (size_t i = 0; i < perm.size(); ++i) {
+    for (int j = 0; j < per; ++j) d2[i * (size_t)per + (size_t)j] = data[(size_t)perm[i] * (size_t)per + (size_t)j];
+    a2[i] = aux[(size_t)perm[i]];
+  }
+  data.swap(d2), aux.swap(a2);
+}
+
+// Bounding box of one flat element (binary64 from the binary32 data the device sees).
+DBox flat_box(int type, const f4* e) {
+  double p[3][3];
+  if (type == G_TRIANGLE) {  // v0, v0 + e1, v0 + e2 with the hoisted edges (triangle.hpp:65-66)
+    for (int k = 0; k < 3; ++k) {
+      const double v0 = (&e[0].x)[k];
+      p[0][k] = v0, p[1][k] = v0 + (double)(&e[1].x)[k], p[2][k] = v0 + (double)(&e[2].x)[k];
+    }
+    return box_of_points(p, 3);
+  }
+  if (type == G_RECT) {  // {a0, a1, b0, b1} {k, axis}
+    int32_t axis;
+    std::memcpy(&axis, &e[1].y, 4);
+    const int ia = axis == PT_AXIS_YZ ? 1 : 0, ib = axis == PT_AXIS_XY ? 1 : 2, ik = axis == PT_AXIS_XY ? 2 : axis == PT_AXIS_XZ ? 1 : 0;
+    p[0][ia] = e[0].x, p[1][ia] = e[0].y, p[0][ib] = e[0].z, p[1][ib] = e[0].w, p[0][ik] = p[1][ik] = e[1].x;
+    return box_of_points(p, 2);
+  }
+  for (int k = 0; k < 3; ++k) p[0][k] = (&e[0].x)[k], p[1][k] = (&e[1].x)[k];  // box: p0, p1
+  return box_of_points(p, 2);
+}
+
 struct Builder {
   std::vector<Group> groups;
   std::vector<f4> sph, mov, rect, tri, box;
+  std::vector<Tree> trees;
+  std::vector<f4> nodes;
+  std::vector<f4> tree_ids;  // grazing index leaves: {g, element index as bits} per triangle
+  double flat_extent = 0;
   PackedScene& out;
   explicit Builder(PackedScene& o) : out(o) {}
 
@@ -123,13 +254,13 @@ struct Builder {
   void flush(Segment& s) {
     if (!s.sph.empty()) {
       Group g {};
-      g.type = G_SPHERE, g.begin = (int32_t)out.sphere_aux.size();
+      g.type = G_SPHERE, g.begin = (int32_t)out.sphere_aux.size(), g.tree = g.gtree = -1;
       g.count = emit_spheres(s.sph, false, sph, out.sphere_aux, out.sphere_geo, out.sphere_chunk_open, g.n_open);
       groups.push_back(g);
     }
     for (auto& c : s.classes) {
       Group g {};
-      g.type = G_MOVING_SPHERE, g.begin = (int32_t)out.moving_aux.size();
+      g.type = G_MOVING_SPHERE, g.begin = (int32_t)out.moving_aux.size(), g.tree = g.gtree = -1;
       g.count = emit_spheres(c.items, true, mov, out.moving_aux, out.moving_geo, out.moving_chunk_open, g.n_open);
       g.time0 = c.time0, g.den = c.time1 - c.time0;
       groups.push_back(g);
@@ -137,6 +268,7 @@ struct Builder {
     if (!s.rect_aux.empty()) {
       Group g {};
       g.type = G_RECT, g.begin = (int32_t)out.rect_aux.size(), g.count = (int32_t)s.rect_aux.size();
+      flat_tree(g, s.rect, s.rect_aux, 2);
       groups.push_back(g);
       rect.insert(rect.end(), s.rect.begin(), s.rect.end());
       out.rect_aux.insert(out.rect_aux.end(), s.rect_aux.begin(), s.rect_aux.end());
@@ -144,6 +276,7 @@ struct Builder {
     if (!s.tri_aux.empty()) {
       Group g {};
       g.type = G_TRIANGLE, g.begin = (int32_t)out.tri_aux.size(), g.count = (int32_t)s.tri_aux.size();
+      flat_tree(g, s.tri, s.tri_aux, 3);
       groups.push_back(g);
       tri.insert(tri.end(), s.tri.begin(), s.tri.end());
       out.tri_aux.insert(out.tri_aux.end(), s.tri_aux.begin(), s.tri_aux.end());
@@ -151,11 +284,77 @@ struct Builder {
     if (!s.box_aux.empty()) {
       Group g {};
       g.type = G_BOX, g.begin = (int32_t)out.box_aux.size(), g.count = (int32_t)s.box_aux.size();
+      flat_tree(g, s.box, s.box_aux, 2);
       groups.push_back(g);
       box.insert(box.end(), s.box.begin(), s.box.end());
       out.box_aux.insert(out.box_aux.end(), s.box_aux.begin(), s.box_aux.end());
     }
     s = Segment {};
+  }
+
+  // A flat group worth culling: k-d order its elements (the winner rule is order independent, pt_packed.h), hang the
+  // leaves of kFlatChunk elements under a box tree and, for triangles, build the grazing index.
+  template <typename Aux> void flat_tree(Group& g, std::vector<f4>& data, std::vector<Aux>& aux, int per) {
+    g.tree = -1, g.gtree = -1;
+    const size_t n = aux.size();
+    if (n < (size_t)kFlatTreeMin) return;
+    std::vector<DBox> boxes(n);
+    std::vector<std::array<double, 3>> mid(n);
+    for (size_t i = 0; i < n; ++i) {
+      boxes[i] = flat_box(g.type, data.data() + i * (size_t)per);
+      for (size_t k = 0; k < 3; ++k) mid[i][k] = boxes[i].open ? 0.0 : 0.5 * boxes[i].lo[k] + 0.5 * boxes[i].hi[k];
+    }
+    std::vector<int> perm(n);
+    for (size_t i = 0; i < n; ++i) perm[i] = (int)i;
+    kd_order_aligned(perm, mid, 0, n, (size_t)kFlatChunk);
+    permute_flat(data, aux, perm, per);
+    std::vector<DBox> ordered(n);
+    for (size_t i = 0; i < n; ++i) ordered[i] = boxes[(size_t)perm[i]];
+    g.tree = (int32_t)trees.size();
+    trees.push_back(build_tree(ordered, (size_t)kFlatChunk, nodes, &flat_extent));
+    if (g.type != G_TRIANGLE) return;
+    // GRAZING INDEX: g = cross(e1, e2) / (|e1| |e2|) per triangle, sign-normalised (only |d . g| matters); a triangle
+    // with a zero or non-finite edge has a = 0 or lives in an open leaf (always visited) and needs no entry.
+    std::vector<int> members;
+    std::vector<std::array<double, 3>> gv(n);
+    for (size_t i = 0; i < n; ++i) {
+      const f4* e = data.data() + i * 3;
+      const double e1[3] = { e[1].x, e[1].y, e[1].z }, e2[3] = { e[2].x, e[2].y, e[2].z };
+      const double l1 = std::sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]), l2 = std::sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+      const double den = l1 * l2;
+      gv[i] = { 0, 0, 0 };
+      if (!(den > 0) || !std::isfinite(den)) continue;
+      double c[3] = { (e1[1] * e2[2] - e1[2] * e2[1]) / den, (e1[2] * e2[0] - e1[0] * e2[2]) / den, (e1[0] * e2[1] - e1[1] * e2[0]) / den };
+      int big = 0;
+      for (int k = 1; k < 3; ++k)
+        if (std::fabs(c[k]) > std::fabs(c[big])) big = k;
+      if (c[big] < 0) c[0] = -c[0], c[1] = -c[1], c[2] = -c[2];
+      gv[i] = { c[0], c[1], c[2] };
+      members.push_back((int)i);
+    }
+    if (members.empty()) return;
+    kd_order_aligned(members, gv, 0, members.size(), (size_t)kFlatChunk);
+    std::vector<DBox> gboxes(members.size());
+    for (size_t i = 0; i < members.size(); ++i) {
+      const double p[1][3] = { { gv[(size_t)members[i]][0], gv[(size_t)members[i]][1], gv[(size_t)members[i]][2] } };
+      gboxes[i] = box_of_points(p, 1);
+    }
+    Tree gt = build_tree(gboxes, (size_t)kFlatChunk, nodes, nullptr);
+    gt.leaf_ids = (int32_t)tree_ids.size();
+    for (size_t i = 0; i < members.size(); ++i) {
+      const int32_t id = g.begin + members[i];
+      f4 e { (float)gv[(size_t)members[i]][0], (float)gv[(size_t)members[i]][1], (float)gv[(size_t)members[i]][2], 0.f };
+      std::memcpy(&e.w, &id, 4);
+      tree_ids.push_back(e);
+    }
+    while (tree_ids.size() % (size_t)kFlatChunk) {
+      f4 e { 0.f, 0.f, 0.f, 0.f };
+      const int32_t none = -1;
+      std::memcpy(&e.w, &none, 4);
+      tree_ids.push_back(e);
+    }
+    g.gtree = (int32_t)trees.size();
+    trees.push_back(gt);
   }
 };
 
@@ -441,7 +640,7 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
         }
         b.flush(seg);
         Group g {};
-        g.type = G_MEDIUM, g.begin = (int32_t)out.media.size(), g.count = 1;
+        g.type = G_MEDIUM, g.begin = (int32_t)out.media.size(), g.count = 1, g.tree = g.gtree = -1;
         b.groups.push_back(g);
         out.media.push_back(r);
         break;
@@ -471,6 +670,11 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   out.off_rect = append(out.blob, b.rect.data(), b.rect.size() * sizeof(f4));
   out.off_triangle = append(out.blob, b.tri.data(), b.tri.size() * sizeof(f4));
   out.off_box = append(out.blob, b.box.data(), b.box.size() * sizeof(f4));
+  out.off_trees = append(out.blob, b.trees.data(), b.trees.size() * sizeof(Tree));
+  out.off_nodes = append(out.blob, b.nodes.data(), b.nodes.size() * sizeof(f4));
+  out.off_tree_ids = append(out.blob, b.tree_ids.data(), b.tree_ids.size() * sizeof(f4));
+  out.n_trees = (uint32_t)b.trees.size();
+  out.flat_extent = (float)b.flat_extent;
   {
     // until compute_cull_boxes() has run for a camera, every chunk is scanned
     CullBoxes none;

@@ -22,6 +22,8 @@ struct PackedScene {
   std::vector<unsigned char> blob;
   uint32_t n_groups = 0;
   uint32_t off_groups = 0, off_sphere = 0, off_moving = 0, off_rect = 0, off_triangle = 0, off_box = 0;
+  uint32_t off_trees = 0, off_nodes = 0, off_tree_ids = 0, n_trees = 0;
+  float flat_extent = 0.f;
   uint32_t off_sphere_box = 0, off_moving_box = 0;  // [kCullSets][chunks][2] float4 each, "no culling" until set
   std::vector<SphereGeo> sphere_geo, moving_geo;    // indexed like sphere_aux / moving_aux
   std::vector<unsigned char> sphere_chunk_open, moving_chunk_open;  // 1: chunk is never culled (outsized spheres)

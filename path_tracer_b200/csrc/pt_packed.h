@@ -56,6 +56,26 @@ constexpr int kCullSets = 4;  // box sets per origin class; the last one is "no 
 PT_HD inline int sphere_slot(int i) { return ((i >> 4) << 5) | (i & 15); }  // float4 index of static sphere i
 PT_HD inline int moving_slot(int i) { return ((i >> 4) << 6) | (i & 15); }  // {c0, r*r}; {c1 - c0} is 32 further
 
+// Rectangles, triangles and boxes ("flat" groups) with at least kFlatTreeMin elements are k-d ordered too, in
+// leaves of kFlatChunk consecutive elements under a TREE of bounding boxes (kTreeFan children per inner
+// node, at most kTreeLevels box levels, the top level a plain list): a ray only tests the leaves whose
+// box -- grown by a margin relative to its distance from the ray origin -- it crosses ("flat culling" in
+// pt_prims.cuh; the proof is in DESIGN.md).  Triangle groups carry a second tree over the triangles'
+// scaled NORMALS (the "grazing index"): the reference's Moller-Trumbore arithmetic is noise for a ray that
+// lies almost in a triangle's plane, and such (ray, triangle) pairs -- for which no geometric margin holds --
+// are found there and tested exactly.
+constexpr int kFlatChunk = 8;
+constexpr int kTreeFan = 16;
+constexpr int kTreeLevels = 3;
+constexpr int kFlatTreeMin = 33;
+
+struct Tree {  // 32 bytes
+  int32_t levels;    // box levels in use (1 .. kTreeLevels); level 0 = leaves
+  int32_t off[3];    // float4 index of level l's boxes in the node array ({lo} {hi} per node)
+  int32_t n[3];      // nodes at level l; node j of level l + 1 covers nodes 16 j .. 16 j + 15 of level l
+  int32_t leaf_ids;  // grazing index only: float4 index of the leaves' triangle lists (kFlatChunk x {g, element index; -1 = none} per leaf)
+};
+
 struct Group {  // 32 bytes
   int32_t type;
   int32_t begin;  // first element, in elements of this kind's array
@@ -63,7 +83,8 @@ struct Group {  // 32 bytes
   float time0;    // G_MOVING_SPHERE: the class's time0
   float den;      // G_MOVING_SPHERE: time1 - time0 (sphere.hpp:55)
   int32_t n_open; // sphere groups: the first n_open elements are OUTSIZED spheres in chunks of their own that are never culled
-  int32_t pad[2];
+  int32_t tree;   // flat groups: index of the group's box tree (leaf c = elements begin + 8 c ...), -1 = scanned directly
+  int32_t gtree;  // triangle groups with a tree: index of the grazing index, -1 = none
 };
 
 // Unified object id carried by the scan: kind in the top bits.
@@ -115,6 +136,9 @@ struct SceneDesc {
   uint32_t stage_bytes;       // blob + the side tables that follow it in the arena (aux, media, keys, object ids, materials)
   uint32_t n_groups;
   uint32_t off_groups, off_sphere, off_moving, off_rect, off_triangle, off_box;
+  uint32_t off_trees, off_nodes, off_tree_ids, n_trees;  // flat groups' trees: Tree[], float4 node boxes, float4 grazing-index leaves
+  uint32_t flat_cull;         // 0: ignore the trees (every flat object is tested: pt_debug_set_cull(0))
+  float flat_extent;          // max |coordinate| over the flat objects under a tree (the slab test's rounding allowance)
   uint32_t n_objects;         // reference n_hittables (for work accounting)
   // chunk boxes: float4 {lo} {hi} per chunk, [kCullSets][n_chunks][2] per sphere kind; rewritten when the
   // camera's shutter interval changes (the boxes of moving spheres cover their sweep over it)

@@ -303,9 +303,13 @@ constexpr float kCullInvMax = 1.152921504606847e18f;  // 2^60
 constexpr float kCullDirMin = 9.5367431640625e-7f;    // 2^-20
 constexpr float kCullDirMax = 1048576.f;              // 2^20
 PT_DEV float rcp_fast(float x) {
+#ifdef __CUDACC__
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#else
+  return 1.0f / x;
+#endif
 }
 // Returns the box set of this ray.
 PT_DEV int make_cull_ray(const SceneDesc& sc, const Ray& r, CullRay& c) {
@@ -434,38 +438,232 @@ PT_DEV void scan_spheres(const SceneDesc& sc, const float4* __restrict__ data, c
                                              act, type, best);
 }
 
-// Rectangles, triangles and boxes of one group: elements first, first + step, ... (running closest as the
-// upper bound, like the reference's loop).
-template <bool kSmem>
-PT_DEV void scan_flat_group(const SceneDesc& sc, const SceneView& sv, const Group& g, const Ray& r, int first, int step,
+// Rectangles, triangles or boxes: elements first, first + step, ... below `end` (running closest as the upper
+// bound, like the reference's loop).
+template <bool kSmem, typename Keys>
+PT_DEV void scan_flat_range(const Keys& sc, const float4* __restrict__ data, int type, int first, int end, int step, const Ray& r,
                             Best& best) {
-  const int end = g.begin + g.count;
-  if (g.type == G_RECT) {
+  if (type == G_RECT) {
     for (int i = first; i < end; i += step) {
-      const float4 q0 = ld4<kSmem>(sv.rect + 2 * i);
-      const float4 q1 = ld4<kSmem>(sv.rect + 2 * i + 1);
+      const float4 q0 = ld4<kSmem>(data + 2 * i);
+      const float4 q1 = ld4<kSmem>(data + 2 * i + 1);
       float t, ra, rb;
       if (rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, best.t, t, ra, rb))
         consider_le(sc, best, t, make_id(G_RECT, i));
     }
-  } else if (g.type == G_TRIANGLE) {
+  } else if (type == G_TRIANGLE) {
     for (int i = first; i < end; i += step) {
-      const float4 v0 = ld4<kSmem>(sv.triangle + 3 * i);
-      const float4 e1 = ld4<kSmem>(sv.triangle + 3 * i + 1);
-      const float4 e2 = ld4<kSmem>(sv.triangle + 3 * i + 2);
+      PT_STAT(triangle_tests);
+      const float4 v0 = ld4<kSmem>(data + 3 * i);
+      const float4 e1 = ld4<kSmem>(data + 3 * i + 1);
+      const float4 e2 = ld4<kSmem>(data + 3 * i + 2);
       float t;
       if (triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, best.t, t))
         consider_le(sc, best, t, make_id(G_TRIANGLE, i));
     }
-  } else if (g.type == G_BOX) {
+  } else if (type == G_BOX) {
     for (int i = first; i < end; i += step) {
-      const float4 p0 = ld4<kSmem>(sv.box + 2 * i);
-      const float4 p1 = ld4<kSmem>(sv.box + 2 * i + 1);
+      const float4 p0 = ld4<kSmem>(data + 2 * i);
+      const float4 p1 = ld4<kSmem>(data + 2 * i + 1);
       float t, ra, rb;
       if (box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, best.t, t, ra, rb) >= 0)
         consider_le(sc, best, t, make_id(G_BOX, i));
     }
   }
+}
+PT_DEV bool has_tree(const SceneDesc& sc, const Group& g) { return g.tree >= 0 && sc.flat_cull != 0u; }
+PT_DEV const float4* flat_data(const SceneView& sv, int type) {
+  return type == G_RECT ? sv.rect : type == G_TRIANGLE ? sv.triangle : sv.box;
+}
+template <bool kSmem>
+PT_DEV void scan_flat_group(const SceneDesc& sc, const SceneView& sv, const Group& g, const Ray& r, int first, int step,
+                            Best& best) {
+  scan_flat_range<kSmem>(sc, flat_data(sv, g.type), g.type, first, g.begin + g.count, step, r, best);
+}
+
+// FLAT CULLING.  A flat group with a tree (pt_packed.h) is scanned leaf by leaf, and only the leaves whose
+// box the ray crosses.  What has to hold, as for the sphere chunks: "the reference accepts element i at
+// parameter t" => "the box test of every node above i passes".  DESIGN.md ("flat culling") shows that the
+// point o + t d of an accepted hit lies within
+//     M = kFlatRel * far + kFlatAbs * (max |o_k| + extent),   far = distance from o to the box's far corner,
+// of the element's bounding box -- for a rectangle or a box side because the reference itself checks the hit
+// point against the bounds (rectangle.hpp:38-41), for a triangle as long as the Moller-Trumbore determinant
+// satisfies |a| >= kGrazeTau |d| |e1| |e2| (the residual of the float solution in the exact equations is
+// 24 u |s| |d| |e1| |e2| / |a|, u = 2^-24).  Every node is therefore tested with its box grown by M (M only
+// grows towards the root, so a crossed leaf has crossed ancestors).  Rays whose direction or origin is out
+// of the range the slab test is proven for are not culled at all (FlatRay::ok).
+// GRAZING INDEX.  Below that determinant bound the reference's u, v and t are rounding noise and it may
+// "hit" a triangle the ray is nowhere near.  Such pairs satisfy |d . g| < (kGrazeTau + 7 u) |d| with g =
+// cross(e1, e2) / (|e1| |e2|): they are found in a second tree over the g vectors and tested exactly, box
+// or no box.  (Testing a triangle twice is harmless: the winner rule is idempotent.)
+#ifndef PT_FLAT_REL  // (overridden only by the sensitivity experiments of tests/host: do mismatches appear when they should?)
+#define PT_FLAT_REL 3.2e-3f
+#define PT_FLAT_ABS 4.0e-6f
+#define PT_GRAZE_TAU 4.8828125e-4f
+#endif
+constexpr float kFlatRel = PT_FLAT_REL;
+constexpr float kFlatAbs = PT_FLAT_ABS;
+constexpr float kGrazeTau = PT_GRAZE_TAU;                     // 2^-11
+constexpr float kGrazeTauDev = kGrazeTau + 64.f * 5.9604645e-8f;  // + the rounding of g and of the interval product
+struct FlatRay {
+  CullRay c;
+  float eabs;  // kFlatAbs * (max |o_k| + extent)
+  float taud;  // grazing threshold: kGrazeTauDev * |d|, rounded up
+  bool ok;     // false: this ray visits every leaf
+};
+PT_DEV float sqrt_fast(float x) {
+#ifdef __CUDACC__
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+PT_DEV float graze_threshold(const Ray& r) {
+  return kGrazeTauDev * 1.0001f * sqrt_fast(__fmaf_rn(r.d.x, r.d.x, __fmaf_rn(r.d.y, r.d.y, r.d.z * r.d.z)));
+}
+PT_DEV FlatRay make_flat_ray(float flat_extent, const Ray& r) {
+  FlatRay f;
+  const float dmax = fmaxf(fmaxf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z));
+  const float omax = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z));
+  // (a ray with an exactly zero direction component lies IN the planes k = o_k: a rectangle or box side there has
+  // t = 0 / 0 = NaN, which the reference accepts wherever the rectangle is, rectangle.hpp:35-41 -- such rays, NaN
+  // and far-out origins, and directions the clamped reciprocal does not cover are never culled)
+  f.ok = dmax >= kCullDirMin && dmax <= kCullDirMax && omax <= 1.0e15f && r.o.x == r.o.x && r.o.y == r.o.y && r.o.z == r.o.z &&
+         r.d.x == r.d.x && r.d.y == r.d.y && r.d.z == r.d.z && r.d.x != 0.f && r.d.y != 0.f && r.d.z != 0.f;
+  f.c.ix = fminf(fmaxf(rcp_fast(r.d.x), -kCullInvMax), kCullInvMax);
+  f.c.iy = fminf(fmaxf(rcp_fast(r.d.y), -kCullInvMax), kCullInvMax);
+  f.c.iz = fminf(fmaxf(rcp_fast(r.d.z), -kCullInvMax), kCullInvMax);
+  f.c.qx = -(r.o.x * f.c.ix), f.c.qy = -(r.o.y * f.c.iy), f.c.qz = -(r.o.z * f.c.iz);
+  f.eabs = kFlatAbs * (omax + flat_extent);
+  f.taud = graze_threshold(r);
+  return f;
+}
+// SIGN BIT set <=> the ray crosses the node's box, grown by M, between t = 0 and tmax.
+template <bool kSmem> PT_DEV uint32_t flat_node_bits(const float4* __restrict__ box, const FlatRay& f, const Ray& r, float tmax) {
+  PT_STAT(flat_nodes);
+  const float4 lo = ld4<kSmem>(box), hi = ld4<kSmem>(box + 1);
+  const float fx = fmaxf(fabsf(r.o.x - lo.x), fabsf(r.o.x - hi.x));
+  const float fy = fmaxf(fabsf(r.o.y - lo.y), fabsf(r.o.y - hi.y));
+  const float fz = fmaxf(fabsf(r.o.z - lo.z), fabsf(r.o.z - hi.z));
+  const float far = sqrt_fast(__fmaf_rn(fx, fx, __fmaf_rn(fy, fy, fz * fz)));
+  const float m = __fmaf_rn(kFlatRel, far, f.eabs);
+  const float ax = __fmaf_rn(lo.x - m, f.c.ix, f.c.qx), bx = __fmaf_rn(hi.x + m, f.c.ix, f.c.qx);
+  const float ay = __fmaf_rn(lo.y - m, f.c.iy, f.c.qy), by = __fmaf_rn(hi.y + m, f.c.iy, f.c.qy);
+  const float az = __fmaf_rn(lo.z - m, f.c.iz, f.c.qz), bz = __fmaf_rn(hi.z + m, f.c.iz, f.c.qz);
+  const float t_in = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.f));
+  const float t_out = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+  return __float_as_uint(t_in - t_out) | (f.ok ? 0u : 0x80000000u);
+}
+// SIGN BIT set <=> some g inside the node's box may have |d . g| <= taud (interval product).
+template <bool kSmem> PT_DEV uint32_t graze_node_bits(const float4* __restrict__ box, const V3& d, float taud) {
+  PT_STAT(graze_nodes);
+  const float4 lo = ld4<kSmem>(box), hi = ld4<kSmem>(box + 1);
+  const float x0 = d.x * lo.x, x1 = d.x * hi.x, y0 = d.y * lo.y, y1 = d.y * hi.y, z0 = d.z * lo.z, z1 = d.z * hi.z;
+  const float mn = (fminf(x0, x1) + fminf(y0, y1)) + fminf(z0, z1);
+  const float mx = (fmaxf(x0, x1) + fmaxf(y0, y1)) + fmaxf(z0, z1);
+  return (mn <= taud && mx >= -taud) ? 0x80000000u : 0u;
+}
+
+// Visit the leaves of a tree whose ancestors (and whose own box) all pass `test` (sign bit of its result).
+template <typename Test, typename Leaf>
+PT_DEV void tree_walk(const Tree& t, const float4* __restrict__ nodes, Test test, Leaf leaf) {
+  // levels by name, not by index (a dynamically indexed struct would live in local memory): A = the top list, B = its
+  // children, C = theirs
+  const int top = t.levels - 1;
+  const int off_a = top == 0 ? t.off[0] : top == 1 ? t.off[1] : t.off[2], n_a = top == 0 ? t.n[0] : top == 1 ? t.n[1] : t.n[2];
+  const int off_b = top == 2 ? t.off[1] : t.off[0], n_b = top == 2 ? t.n[1] : t.n[0];
+  const float4* b2 = nodes + off_a;
+  const int n2 = n_a;
+#pragma unroll 1
+  for (int c2 = 0; c2 < n2; c2 += 32) {
+    const int k2 = min(32, n2 - c2);
+    uint32_t m2 = 0;
+#pragma unroll 1
+    for (int k = 0; k < k2; ++k) m2 = __funnelshift_l(test(b2 + 2 * (c2 + k)), m2, 1);
+#pragma unroll 1
+    while (m2) {
+      const int p2 = 31 - __clz((int)m2);
+      m2 &= ~(1u << p2);
+      const int i2 = c2 + (k2 - 1 - p2);
+      if (top == 0) {
+        leaf(i2);
+        continue;
+      }
+      const float4* b1 = nodes + off_b;
+      const int c1 = i2 * kTreeFan, k1 = min(kTreeFan, n_b - c1);
+      uint32_t m1 = 0;
+#pragma unroll 1
+      for (int k = 0; k < k1; ++k) m1 = __funnelshift_l(test(b1 + 2 * (c1 + k)), m1, 1);
+#pragma unroll 1
+      while (m1) {
+        const int p1 = 31 - __clz((int)m1);
+        m1 &= ~(1u << p1);
+        const int i1 = c1 + (k1 - 1 - p1);
+        if (top == 1) {
+          leaf(i1);
+          continue;
+        }
+        const float4* b0 = nodes + t.off[0];
+        const int c0 = i1 * kTreeFan, k0 = min(kTreeFan, t.n[0] - c0);
+        uint32_t m0 = 0;
+#pragma unroll 1
+        for (int k = 0; k < k0; ++k) m0 = __funnelshift_l(test(b0 + 2 * (c0 + k)), m0, 1);
+#pragma unroll 1
+        while (m0) {
+          const int p0 = 31 - __clz((int)m0);
+          m0 &= ~(1u << p0);
+          leaf(c0 + (k0 - 1 - p0));
+        }
+      }
+    }
+  }
+}
+
+// One leaf of the grazing index: its triangles, wherever they lie.
+template <bool kSmem, typename Keys>
+PT_DEV void scan_graze_leaf(const Keys& sc, const float4* __restrict__ triangles, const float4* __restrict__ entries, int first, int step,
+                            const Ray& r, float taud, Best& best) {
+  for (int j = first; j < kFlatChunk; j += step) {
+    const float4 e = ld4<kSmem>(entries + j);
+    const int i = __float_as_int(e.w);
+    PT_STAT(graze_tests);
+    if (i >= 0 && fabsf(__fmaf_rn(r.d.x, e.x, __fmaf_rn(r.d.y, e.y, r.d.z * e.z))) <= taud)
+      scan_flat_range<kSmem>(sc, triangles, G_TRIANGLE, i, i + 1, 1, r, best);
+  }
+}
+
+// A flat group with a tree for one ray, in place (lane kernel, sequential fallback, LATE): member `first` of a
+// team of `step` takes every step-th element of each visited leaf.  Out of line and by value (one copy per
+// kernel, nothing forced into local memory).
+struct FlatTrees {
+  const float4* data;  // the group's kind's array
+  const Tree* trees;
+  const float4* nodes;
+  const float4* ids;
+  float extent;
+};
+PT_DEV FlatTrees flat_trees(const SceneDesc& sc, const SceneView& sv, int type) {
+  return FlatTrees { flat_data(sv, type), sv.trees, sv.nodes, sv.tree_ids, sc.flat_extent };
+}
+template <bool kSmem>
+__device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, Ray r, int first, int step, Best best) {
+  const FlatRay fr = make_flat_ray(ft.extent, r);
+  const Tree t = ft.trees[g.tree];
+  tree_walk(
+      t, ft.nodes, [&](const float4* box) { return flat_node_bits<kSmem>(box, fr, r, best.t); },
+      [&](int leaf) {
+        const int b = g.begin + leaf * kFlatChunk;
+        scan_flat_range<kSmem>(sc, ft.data, g.type, b + first, min(b + kFlatChunk, g.begin + g.count), step, r, best);
+      });
+  if (g.gtree >= 0 && fr.ok) {
+    const Tree gt = ft.trees[g.gtree];
+    tree_walk(
+        gt, ft.nodes, [&](const float4* box) { return graze_node_bits<kSmem>(box, r.d, fr.taud); },
+        [&](int leaf) { scan_graze_leaf<kSmem>(sc, ft.data, ft.ids + gt.leaf_ids + leaf * kFlatChunk, first, step, r, fr.taud, best); });
+  }
+  return best;
 }
 
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
@@ -504,7 +702,12 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
         break;
       }
       default:
-        if (act) scan_flat_group<kSmem>(sc, sv, g, r, g.begin + member, team_size, best);
+        if (act) {
+          if (has_tree(sc, g))
+            best = scan_flat_tree<kSmem>(key_table(sc), flat_trees(sc, sv, g.type), g, r, member, team_size, best);
+          else
+            scan_flat_group<kSmem>(sc, sv, g, r, g.begin + member, team_size, best);
+        }
         break;
     }
   }

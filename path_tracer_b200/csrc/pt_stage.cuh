@@ -11,6 +11,7 @@ namespace {
 
 PT_DEV unsigned int ld_volatile_u32(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
 
+#ifdef __CUDACC__
 PT_DEV unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -49,6 +50,8 @@ PT_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+#endif  // __CUDACC__
+
 // ---------------------------------------------------------------- scene view
 struct SceneView {
   const Group* groups;
@@ -59,7 +62,26 @@ struct SceneView {
   const float4* box;
   const float4* sphere_box;  // chunk boxes, set 0 first
   const float4* moving_box;
+  const Tree* trees;         // flat groups' box trees and grazing indices (pt_packed.h)
+  const float4* nodes;       // their boxes
+  const float4* tree_ids;    // grazing index: the leaves' {g, triangle} lists
 };
+// Point the view at the scan blob (in shared or global memory).
+PT_DEV SceneView scene_view(const SceneDesc& sc, const unsigned char* blob_base) {
+  SceneView sv;
+  sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
+  sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
+  sv.moving = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
+  sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
+  sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
+  sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
+  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
+  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
+  sv.trees = reinterpret_cast<const Tree*>(blob_base + sc.off_trees);
+  sv.nodes = reinterpret_cast<const float4*>(blob_base + sc.off_nodes);
+  sv.tree_ids = reinterpret_cast<const float4*>(blob_base + sc.off_tree_ids);
+  return sv;
+}
 
 template <bool kSmem> PT_DEV float4 ld4(const float4* p) {
   if constexpr (kSmem)

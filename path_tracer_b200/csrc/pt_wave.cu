@@ -111,6 +111,7 @@ constexpr int kFineBoxes = PT_FINE_BOXES;            // ... BOXES: a ray's chunk
 constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in runs of this many
 constexpr int kMaxBoxBlocks = 64;
 constexpr int kMaxFlats = 256;
+constexpr int kMaxTreeGroups = 8;
 static_assert(kWavePool <= 1024, "an item packs the pool slot into 10 bits");
 
 struct WavePool {
@@ -133,9 +134,14 @@ struct WavePool {
   int n_next;      // length of list_a being built
   int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
   int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
+  int n_items_f;   // (ray, leaf) items of the flat groups with a tree
+  int cap_s, cap_m, cap_f;  // shares of the item list: static items from the front, flat items behind them, moving ones from the back
+  int n_tgroups;   // flat groups with a tree in front of the first constant_medium (traversed per ray in BOXES)
+  int tgroups[kMaxTreeGroups];
   int free_count;
   int pixel_dry;   // the pixel queue has run dry
   int service;     // hand-off service: 0 = keep polling, 1 = every producer is done and the queue is empty
+  int blocks_ok;   // the sphere chunks fit the block table (else no short rounds)
   int n_blocks;    // fine BOXES: blocks of <= kFineBoxes chunks over all sphere groups (0: too many, coarse only)
   int4 blocks[kMaxBoxBlocks];  // {group, first chunk, chunks, 0}
   int n_flats;     // rectangles, triangles and boxes in FRONT of the first constant_medium: tested one thread per (ray, object)
@@ -172,6 +178,69 @@ PT_DEV Best unpack_winner(const SceneDesc& sc, unsigned long long v) {
   return best;
 }
 
+}  // namespace
+
+namespace {
+// One (ray, leaf) item of a flat group with a tree -- {slot | tree group << 10, leaf | grazing-index flag << 31} --
+// for the elements first, first + step, ... of the leaf.
+template <bool kSmem, typename Keys>
+PT_DEV void flat_item_scan(const Keys& sc, const FlatTrees& ft, const Group& g, uint32_t leaf_word, const Ray& ray, int first, int step,
+                           Best& b) {
+  const int leaf = (int)(leaf_word & 0x7fffffffu);
+  if (leaf_word >> 31) {
+    const Tree gt = ft.trees[g.gtree];
+    scan_graze_leaf<kSmem>(sc, ft.data, ft.ids + gt.leaf_ids + leaf * kFlatChunk, first, step, ray, graze_threshold(ray), b);
+  } else {
+    const int base = g.begin + leaf * kFlatChunk;
+    scan_flat_range<kSmem>(sc, ft.data, g.type, base + first, min(base + kFlatChunk, g.begin + g.count), step, ray, b);
+  }
+}
+// ITEMS: one (ray, leaf) item, merged into the ray's winner.
+template <bool kSmem>
+__device__ __noinline__ void wave_run_flat(WavePool* W, KeyTable kt, FlatTrees ft, Group g, uint2 it, int first, int step) {
+  const int slot = (int)(it.x & 1023u);
+  Ray ray;
+  ray.o = v3(W->ox[slot], W->oy[slot], W->oz[slot]);
+  ray.d = v3(W->dx[slot], W->dy[slot], W->dz[slot]);
+  ray.tm = W->tm[slot];
+  Best b { kInf, -1 };
+  flat_item_scan<kSmem>(kt, ft, g, it.y, ray, first, step, b);
+  if (b.id >= 0) atomicMin(&W->best64[slot], pack_winner(b.t, key_of(kt, b.id)));
+}
+// BOXES for one ray and one flat group with a tree: every leaf whose (grown) box the ray crosses, and every leaf of
+// the grazing index that may hold a triangle the ray grazes, becomes an item; what does not fit into the group's
+// share of the item list is scanned in place and folded into the ray's winner `v`.  Out of line: the hot loops of
+// the sphere path must own the instruction cache and the registers.
+template <bool kSmem>
+__device__ __noinline__ unsigned long long wave_emit_flat(WavePool* W, KeyTable kt, FlatTrees ft, Group g, uint32_t slot_tg, Ray ray,
+                                                          int item_base, int cap_f, unsigned long long* counters,
+                                                          unsigned long long v) {
+  const FlatRay fr = make_flat_ray(ft.extent, ray);
+  auto emit = [&](int leaf, uint32_t graze) {
+    const uint2 it = make_uint2(slot_tg, (uint32_t)leaf | (graze << 31));
+    const int at = atomicAdd(&W->n_items_f, 1);
+    if (at < cap_f) {
+      W->items[item_base + at] = it;
+    } else {
+      if (counters) atomicAdd(counters + 15, 1ull);  // stats: items scanned in place
+      Best b { kInf, -1 };
+      flat_item_scan<kSmem>(kt, ft, g, it.y, ray, 0, 1, b);
+      if (b.id >= 0) {
+        const unsigned long long w64 = pack_winner(b.t, key_of(kt, b.id));
+        if (w64 < v) v = w64;
+      }
+    }
+  };
+  const Tree t = ft.trees[g.tree];
+  tree_walk(
+      t, ft.nodes, [&](const float4* box) { return flat_node_bits<kSmem>(box, fr, ray, kInf); }, [&](int leaf) { emit(leaf, 0u); });
+  if (g.gtree >= 0 && fr.ok) {
+    const Tree gt = ft.trees[g.gtree];
+    tree_walk(
+        gt, ft.nodes, [&](const float4* box) { return graze_node_bits<kSmem>(box, ray.d, fr.taud); }, [&](int leaf) { emit(leaf, 1u); });
+  }
+  return v;
+}
 }  // namespace
 
 template <bool kSmem>
@@ -215,18 +284,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   if constexpr (kSmem) mbar_wait(&stage_bar, 0);
   const SceneDesc& sc = staged_scene;
   WavePool& W = *reinterpret_cast<WavePool*>(smem_blob);
-  SceneView sv;
-  sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
-  sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
-  sv.moving = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
-  sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
-  sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
-  sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
-  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
-  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
+  const SceneView sv = scene_view(sc, blob_base);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
-  const unsigned long long t_give_up = globaltimer_ns() + 30000000000ull;  // watchdog against a hung queue
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rot = lane & (kSphereChunk - 1);
   const pt_camera& cam = p.cam;
@@ -238,6 +298,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   const int n_groups = (int)sc.n_groups;
   unsigned int n_scans = 0;
 
+  int cap_s = 0, cap_m = 0, cap_f = 0, n_tgroups = 0;  // shares of the item list, flat groups with a tree (set once the tables exist)
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
   // The first p.express_positions positions of the queue (the most expensive tiles of the LPT order) belong to the
   // express CTAs, which trace them in short rounds from the start; everybody else begins behind them.
@@ -268,27 +329,54 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       return true;
     }
   };
-  // Take the next entry of the hand-off queue: its index, or -1 when there is none right now.
-  auto take_heavy = [&]() -> int {
-    unsigned int h = ld_volatile_u32(hq.ctrl + 0);
+  // The hand-off queue is a bounded multi-producer / multi-consumer RING (pt_kernel.h): position `pos` lives in slot
+  // pos mod cap, whose sequence word says what the slot is ready for -- pos: to be written, pos + 1: to be read, pos +
+  // cap: the next lap.  Nobody ever waits: a full ring keeps the pixel where it is, an empty one (or an entry still
+  // being written) is polled again next time.
+  // Claim the next entry: its position (read it, then release_heavy()), or false when there is none right now.
+  auto take_heavy = [&](unsigned int& pos_out) -> bool {
+    unsigned int pos = ld_volatile_u32(hq.ctrl + 0);
     for (int attempt = 0; attempt < 8; ++attempt) {
-      const unsigned int t = min(ld_volatile_u32(hq.ctrl + 1), hq.cap);
-      if (h >= t) return -1;
-      const unsigned int seen = atomicCAS(hq.ctrl + 0, h, h + 1u);
-      if (seen == h) {
-        while (ld_volatile_u32(hq.ready + h) != hq.stamp) {
-          if (globaltimer_ns() > t_give_up) {
-            if (p.counters) atomicExch(p.counters + 4, 1ull);  // reported as an error by the host
-            return -1;
-          }
-          __nanosleep(100);
+      const int dif = (int)(ld_volatile_u32(hq.ready + (pos & (hq.cap - 1u))) - (pos + 1u));
+      if (dif == 0) {
+        const unsigned int seen = atomicCAS(hq.ctrl + 0, pos, pos + 1u);
+        if (seen == pos) {
+          __threadfence();
+          pos_out = pos;
+          return true;
         }
-        __threadfence();
-        return (int)h;
+        pos = seen;
+      } else if (dif < 0) {
+        return false;
+      } else {
+        pos = ld_volatile_u32(hq.ctrl + 0);
       }
-      h = seen;
     }
-    return -1;
+    return false;
+  };
+  auto release_heavy = [&](unsigned int pos) {
+    __threadfence();
+    *reinterpret_cast<volatile unsigned int*>(hq.ready + (pos & (hq.cap - 1u))) = pos + hq.cap;
+  };
+  // Reserve a slot for a pixel that leaves: its position (write the entry, then publish_heavy()), or false: ring full.
+  auto reserve_heavy = [&](unsigned int& pos_out) -> bool {
+    unsigned int pos = ld_volatile_u32(hq.ctrl + 1);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+      const int dif = (int)(ld_volatile_u32(hq.ready + (pos & (hq.cap - 1u))) - pos);
+      if (dif == 0) {
+        const unsigned int seen = atomicCAS(hq.ctrl + 1, pos, pos + 1u);
+        if (seen == pos) {
+          pos_out = pos;
+          return true;
+        }
+        pos = seen;
+      } else if (dif < 0) {
+        return false;
+      } else {
+        pos = ld_volatile_u32(hq.ctrl + 1);
+      }
+    }
+    return false;
   };
   // Append the live slots of this warp to the next scan list (one shared-memory atomic per warp).
   auto append = [&](bool alive, bool own, int slot) {
@@ -332,7 +420,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       const int top = 31 - __clz((int)hits);
       hits &= ~(1u << top);
       const int chunk = cb + (nb - 1 - top);
-      if (at < (moving ? kWaveItemsMoving : kWaveItemsStatic)) {
+      if (at < (moving ? cap_m : cap_s)) {
         W.items[moving ? kWaveItems - 1 - at : at] = make_uint2((uint32_t)slot | ((uint32_t)chunk << 10), __float_as_uint(f));
       } else {
         if (p.counters) atomicAdd(p.counters + 15, 1ull);  // stats: items scanned in place (tests check that it happens)
@@ -343,6 +431,17 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
       ++at;
     }
+  };
+
+  // (ray, leaf) items of the flat groups with a tree: flat_item_scan / wave_emit_flat above the kernel
+  auto run_flat_item = [&](const uint2 it, int first, int step) {
+    const Group g = sv.groups[W.tgroups[it.x >> 10]];
+    wave_run_flat<kSmem>(&W, key_table(sc), flat_trees(sc, sv, g.type), g, it, first, step);
+  };
+  auto emit_flat_items = [&](int slot, const Ray& ray, int tg, unsigned long long& v) {
+    const Group g = sv.groups[W.tgroups[tg]];
+    v = wave_emit_flat<kSmem>(&W, key_table(sc), flat_trees(sc, sv, g.type), g, (uint32_t)slot | ((uint32_t)tg << 10), ray, cap_s, cap_f,
+                              p.counters, v);
   };
 
   int mode = 0;  // 0: this CTA's share of the pixel queue (none for an express CTA); 1: hand-off service
@@ -360,14 +459,20 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         W.blocks[nb++] = make_int4(gi, cb, min(kFineBoxes, c_end - cb), 0);
       }
     }
-    W.n_blocks = nb < 0 ? 0 : nb;
+    W.n_blocks = nb < 0 ? 0 : nb, W.blocks_ok = nb >= 0;
     // the flat objects in front of the first medium (as many as fit; the rest stays with the sequential part)
-    int nf = 0, late = n_groups;
+    int nf = 0, nt = 0, late = n_groups;
     for (int gi = 0; gi < n_groups; ++gi) {
       const Group g = sv.groups[gi];
-      if (g.type == G_MEDIUM || ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && nf + 6 * g.count > kMaxFlats)) {
+      const bool flat = g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX;
+      const bool tree = flat && has_tree(sc, g);
+      if (g.type == G_MEDIUM || (flat && !tree && nf + 6 * g.count > kMaxFlats) || (tree && nt == kMaxTreeGroups)) {
         late = gi;
         break;
+      }
+      if (tree) {  // a group with a tree: traversed per ray in BOXES, its leaves become items
+        W.tgroups[nt++] = gi;
+        continue;
       }
       if (g.type == G_RECT || g.type == G_TRIANGLE)
         for (int i = 0; i < g.count; ++i) W.flats[nf++] = make_int2(g.type, g.begin + i);
@@ -375,11 +480,18 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         for (int i = 0; i < g.count; ++i)
           for (int side = 0; side < 6; ++side) W.flats[nf++] = make_int2(G_BOX | (side << 8), g.begin + i);
     }
-    W.n_flats = nf, W.first_late_group = late;
+    W.n_flats = nf, W.first_late_group = late, W.n_tgroups = nt;
+    // shares of the item list (the split of a sphere-only scene is the one measured best on the default scene)
+    const bool has_s = sc.n_sphere_chunks != 0u, has_m = sc.n_moving_chunks != 0u;
+    const int for_spheres = nt == 0 ? kWaveItems : (has_s || has_m) ? kWaveItems / 2 : 0;
+    W.cap_f = kWaveItems - for_spheres;
+    W.cap_s = nt == 0 ? kWaveItemsStatic : has_m ? (has_s ? for_spheres * 3 / 8 : 0) : for_spheres;
+    W.cap_m = for_spheres - W.cap_s;
   }
   if (tid < 8) W.counts[tid] = 0;
-  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
+  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.n_items_f = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
+  cap_s = W.cap_s, cap_m = W.cap_m, cap_f = W.cap_f, n_tgroups = W.n_tgroups;
   if (!express) {  // (an express CTA goes straight to the hand-off service, whose first source is its reserved tiles)
     // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
     const int cap = p.pool_cap;
@@ -410,7 +522,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       const int room = W.free_count, waiting = W.n_next;
       if (room > 0 && ((round & 7u) == 0u || waiting == 0)) {
         __syncthreads();  // everybody has read the two (and decided alike) before anybody changes them
-        int got = -1;
+        bool got = false;
+        unsigned int got_pos = 0u;
         if (tid < room) {
           // an express CTA's first source is the head of the LPT order (reserved for it), then the hand-off queue -- which
           // it serves from the start, whenever it has room
@@ -425,12 +538,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             W.pix[slot] = pixq, W.scans[slot] = -1;  // (never handed off again)
             W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
           } else {
-            got = take_heavy();
+            got = take_heavy(got_pos);
           }
         }
-        if (got >= 0) {
+        if (got) {
           const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
-          const float* e = hq.entries + (size_t)got * kHeavyEntryWords;
+          const float* e = hq.entries + (size_t)(got_pos & (hq.cap - 1u)) * kHeavyEntryWords;
           Ray ray;
           ray.o = v3(__ldcg(e + 4), __ldcg(e + 5), __ldcg(e + 6));
           ray.d = v3(__ldcg(e + 7), __ldcg(e + 8), __ldcg(e + 9));
@@ -443,6 +556,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             const unsigned long long waited = (uint32_t)((uint32_t)globaltimer_ns() - __float_as_uint(__ldcg(e + 17)));
             atomicAdd(p.counters + 12, waited), atomicMax(p.counters + 13, waited);
           }
+          release_heavy(got_pos);
         }
         __syncthreads();
       }
@@ -463,19 +577,17 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         __syncthreads();
         continue;
       }
-      // idle: every producer is done and the queue is empty (or the watchdog fired) => nothing will ever arrive again
+      // idle: every producer is done (the launch is cooperative: every CTA is resident and will report) and every entry
+      // has been claimed => nothing will ever arrive again
       if (tid == 0)
-        W.service = ((ld_volatile_u32(hq.ctrl + 2) >= gridDim.x &&
-                      ld_volatile_u32(hq.ctrl + 0) >= min(ld_volatile_u32(hq.ctrl + 1), hq.cap)) ||
-                     globaltimer_ns() > t_give_up)
-                        ? 1
-                        : 0;
+        W.service = (ld_volatile_u32(hq.ctrl + 2) >= gridDim.x && ld_volatile_u32(hq.ctrl + 0) == ld_volatile_u32(hq.ctrl + 1)) ? 1 : 0;
       __syncthreads();
       if (W.service == 1) break;
       __nanosleep(300);
       continue;  // (the next write of W.service is behind the barrier at the loop top)
     }
-    const bool fine = n <= kFineRays && W.n_blocks > 0;
+    const int units_per_ray = W.n_blocks + n_tgroups;  // short rounds: a ray's sphere chunks in blocks, its flat trees one by one
+    const bool fine = n <= kFineRays && W.blocks_ok && units_per_ray > 0;
 #ifdef PT_PHASE_TIMING
     long long pt_t0 = clock64();
 #define PT_PHASE(k)                                                                                   \
@@ -501,9 +613,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
     } else {
       // one work unit = one ray x (all its chunks | a block of kFineBoxes chunks)
-      const int n_units = fine ? n * W.n_blocks : n;
+      const int n_units = fine ? n * units_per_ray : n;
       for (int w = tid; w < n_units; w += kWaveThreads) {
-        const int e = fine ? w / W.n_blocks : w;
+        const int e = fine ? w / units_per_ray : w;
         const int slot = (int)W.list_a[e];
         const Ray ray = load_ray(slot);
         CullRay cr;
@@ -511,7 +623,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const float a = vdot(ray.d, ray.d);  // sphere.hpp:69
         Best inl { kInf, -1 };
         unsigned long long v = kNoHit64;
-        const int4 blk = fine ? W.blocks[w - e * W.n_blocks] : make_int4(0, 0, 0, 0);
+        const int unit = fine ? w - e * units_per_ray : 0;
+        if (fine && unit >= W.n_blocks) {  // short rounds: one flat tree of the ray
+          emit_flat_items(slot, ray, unit - W.n_blocks, v);
+          if (v != kNoHit64) atomicMin(&W.best64[slot], v);
+          continue;
+        }
+        const int4 blk = fine ? W.blocks[unit] : make_int4(0, 0, 0, 0);
         for (int gi = fine ? blk.x : 0; gi < (fine ? blk.x + 1 : n_groups); ++gi) {
           const Group g = sv.groups[gi];
           if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
@@ -565,13 +683,15 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           Best fb { kInf, -1 };
           for (int gi = 0; gi < W.first_late_group; ++gi) {
             const Group g = sv.groups[gi];
-            if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, fb);
+            if ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && !has_tree(sc, g)) scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, fb);
           }
           if (fb.id >= 0) {
             const unsigned long long w64 = pack_winner(fb.t, key_of(sc, fb.id));
             if (w64 < v) v = w64;
           }
         }
+        if (!fine && n_tgroups != 0)
+          for (int tg = 0; tg < n_tgroups; ++tg) emit_flat_items(slot, ray, tg, v);
         if (v != kNoHit64) atomicMin(&W.best64[slot], v);
       }
     }
@@ -580,7 +700,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 
     // ---- SPHERES: one thread per (ray, chunk) item, or per quarter of one
     if (!sequential_scan) {
-      const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving);
+      const int n_s = min(W.n_items_s, cap_s), n_m = min(W.n_items_m, cap_m), n_f = min(W.n_items_f, cap_f);
 #ifdef PT_PHASE_TIMING
       if (tid == 0 && p.counters) atomicAdd(p.counters + 23, (unsigned long long)(n_s + n_m));
 #endif
@@ -588,8 +708,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         // one index space for both kinds (a thread's items follow each other without a pass boundary in between); the
         // moving items start at a warp boundary so that a warp runs one kind's code
         const int m_base = (n_s + 31) & ~31;
-        for (int i = tid; i < m_base + n_m; i += kWaveThreads) {
-          if (i >= n_s && i < m_base) continue;
+        const int fl_base = (m_base + n_m + 31) & ~31;  // (ray, leaf) items of the flat trees: one thread per leaf
+        for (int i = tid; i < fl_base + n_f; i += kWaveThreads) {
+          if ((i >= n_s && i < m_base) || (i >= m_base + n_m && i < fl_base)) continue;
+          if (i >= fl_base) {
+            run_flat_item(W.items[cap_s + (i - fl_base)], 0, 1);
+            continue;
+          }
           const bool moving = i >= m_base;
           const uint2 it = W.items[moving ? kWaveItems - 1 - (i - m_base) : i];
           const int slot = (int)(it.x & 1023u);
@@ -613,8 +738,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int n_quarters = kParts * (n_s + n_m);
         const int f_base = (n_quarters + 31) & ~31;
         const int n_flats = W.n_flats;
-        for (int w = tid; w < f_base + n * n_flats; w += kWaveThreads) {
-          if (w < n_quarters) {
+        const int fl_base = (f_base + n * n_flats + 31) & ~31;  // flat-tree items: one thread per (leaf, element)
+        for (int w = tid; w < fl_base + kFlatChunk * n_f; w += kWaveThreads) {
+          if (w >= fl_base) {
+            run_flat_item(W.items[cap_s + (w - fl_base) / kFlatChunk], (w - fl_base) % kFlatChunk, kFlatChunk);
+          } else if (w < n_quarters) {
             const int i = w / kParts;
             const bool moving = i >= n_s;
             const uint2 it = W.items[moving ? kWaveItems - 1 - (i - n_s) : i];
@@ -629,7 +757,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
               scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
                                                              0.f, G_SPHERE, b);
             if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
-          } else if (w >= f_base) {
+          } else if (w >= f_base && w < f_base + n * n_flats) {
             const int j = (w - f_base) / n;
             const int2 fo = W.flats[j];
             const int slot = (int)W.list_a[(w - f_base) - j * n];
@@ -655,7 +783,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     PT_PHASE(1)
 
     // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
-    if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0;  // (SHADE builds the next round's list)
+    if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.n_items_f = 0;  // (SHADE builds the next round's list)
     for (int e = tid; e < n; e += kWaveThreads) {
       const int slot = (int)W.list_a[e];
       Best best;
@@ -672,7 +800,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           for (int gi = late; gi < n_groups; ++gi) {
             const Group g = sv.groups[gi];
             if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) {
-              scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, best);
+              if (has_tree(sc, g))
+                best = scan_flat_tree<kSmem>(key_table(sc), flat_trees(sc, sv, g.type), g, ray, 0, 1, best);
+              else
+                scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, best);
             } else if (g.type == G_MEDIUM) {
               float t;
               if (medium_hit_t(sc.media[g.begin], ray, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
@@ -746,11 +877,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           }
         }
         // a heavy pixel leaves for a CTA that runs short rounds, with its complete state
-        if (!new_pixel && own && p.order_mode != 2 && scans > kHeavyBase + heavy_rate * sample &&
-            ld_volatile_u32(hq.ctrl + 1) < hq.cap) {
-          const unsigned int i = atomicAdd(hq.ctrl + 1, 1u);
-          if (i < hq.cap) {
-            float* q = hq.entries + (size_t)i * kHeavyEntryWords;
+        if (!new_pixel && own && p.order_mode != 2 && scans > kHeavyBase + heavy_rate * sample) {
+          unsigned int i = 0u;
+          if (reserve_heavy(i)) {
+            float* q = hq.entries + (size_t)(i & (hq.cap - 1u)) * kHeavyEntryWords;
             __stcg(q + 0, __uint_as_float(pixq)), __stcg(q + 1, __uint_as_float(rng.s));
             __stcg(q + 2, __int_as_float(sample)), __stcg(q + 3, __int_as_float(bounce));
             __stcg(q + 4, ray.o.x), __stcg(q + 5, ray.o.y), __stcg(q + 6, ray.o.z);
@@ -759,7 +889,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             __stcg(q + 14, acc.x), __stcg(q + 15, acc.y), __stcg(q + 16, acc.z);
             __stcg(q + 17, __uint_as_float((uint32_t)globaltimer_ns()));
             __threadfence();
-            *reinterpret_cast<volatile unsigned int*>(hq.ready + i) = hq.stamp;
+            *reinterpret_cast<volatile unsigned int*>(hq.ready + (i & (hq.cap - 1u))) = i + 1u;
+            if (p.counters) atomicAdd(p.counters + 7, 1ull);  // stats: pixels handed off
             new_pixel = true;
           }
         }
@@ -911,8 +1042,11 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     q.scramble = pixels > 1 ? mul % pixels : 1ull;
     if (q.scramble == 0ull) q.scramble = 1ull;
     if (info) info->grid = grid, info->block = kWaveThreads, info->smem_bytes = (int)dyn, info->blocks_per_sm = 1, info->staged = smem, info->team_size = 0;
-    kernel<<<grid, kWaveThreads, dyn, stream>>>(q);
-    return cudaGetLastError();
+    // COOPERATIVE launch: the CTAs wait for each other (the service loop ends when every CTA has reported), so the grid
+    // must be co-resident; launched this way the runtime guarantees it -- or fails the launch -- whatever else is
+    // running on the device (another stream's render, another process).
+    void* args[] = { (void*)&q };
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3((unsigned)kWaveThreads), args, dyn, stream);
   }
   return launch_lane(p, device, grid_override, stream, info);
 }

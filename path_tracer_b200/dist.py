@@ -79,6 +79,7 @@ class DistRenderer:
         self.row_floats = width * 3
         self._peer_ptr = None
         self._fb_ptr = None
+        self._stream = None  # the stream of the last launch(): gather() waits for THAT one
         torch.cuda.set_device(device)
         if world == 1 or mode == "nccl":
             first, count = rank_rows(height, rank, world)
@@ -116,7 +117,8 @@ class DistRenderer:
 
     def launch(self, stream=None):
         """Asynchronous: enqueue this rank's rows on `stream` (torch stream or None = current)."""
-        st = (stream or self.torch.cuda.current_stream()).cuda_stream
+        self._stream = stream or self.torch.cuda.current_stream()
+        st = self._stream.cuda_stream
         ptr, pitch = self.target()
         if self.region.h > 0:
             self.scene.render_region(self.camera, self.width, self.height, self.spp, self.depth, self.region, ptr,
@@ -126,14 +128,17 @@ class DistRenderer:
         """Complete the step: full framebuffer on rank 0 (torch tensor or numpy view), None elsewhere."""
         import torch.distributed as dist
         torch = self.torch
+        launched_on = self._stream or torch.cuda.current_stream()
         if self.mode == "local":
-            torch.cuda.current_stream().synchronize()
+            launched_on.synchronize()
             return self.local
         if self.mode == "nccl":
+            if launched_on != torch.cuda.current_stream():
+                torch.cuda.current_stream().wait_stream(launched_on)  # the collective runs on the current stream
             _, n = rank_rows(self.height, self.rank, self.world)
             return gather_rows(self.local[:n], self.width, self.height, self.rank, self.world)
         # peer: the stores already landed in rank 0's HBM once every rank's kernel retired
-        torch.cuda.current_stream().synchronize()
+        launched_on.synchronize()
         dist.barrier()
         return self.fb_view() if self.rank == 0 else None
 
@@ -151,6 +156,15 @@ class DistRenderer:
 
     def close(self):
         L = self.R.lib()
+        if self.mode == "peer" and self.world > 1:
+            # nobody may still be storing into, or have mapped, rank 0's framebuffer when it is freed
+            import torch.distributed as dist
+            if self._stream is not None:
+                self._stream.synchronize()
+            if self._peer_ptr:
+                L.pt_fb_close(C.c_void_p(self._peer_ptr))
+                self._peer_ptr = None
+            dist.barrier()
         if self._peer_ptr:
             L.pt_fb_close(C.c_void_p(self._peer_ptr))
             self._peer_ptr = None

@@ -173,6 +173,39 @@ def triangle_mesh(aspect=16 / 9, nx=12, nz=6, seed=5):
     return s, _cam(aspect, look_from=(10, 4, 8), vfov=30.0, aperture=0.05, focus=12.0)
 
 
+def c4_mesh(aspect=16 / 9, nx=100, nz=25, seed=4):
+    """BASELINE config 4: ~10 000 triangles -- an nx x nz grid of 4-triangle pyramids (the reference's pyramid
+    pattern, main.cpp:113-126) on a two-triangle ground, Lambertian checker / solid with some metal and glass
+    faces; image textures only on a few spheres and an xy_rect (triangles do not write u, v: triangle.hpp:94-98).
+    Pyramid placement and apex heights come from numpy's RandomState (not LocalPseudoRNG): oracle and GPU get
+    the same vectors either way."""
+    rs = np.random.RandomState(seed)
+    f = np.float32
+    s = Scene()
+    ground = s.lambertian(s.checker((0.2, 0.3, 0.1), (0.9, 0.9, 0.9)))
+    img = s.image(test_image(64, 32, 9))
+    palette = [s.lambertian(tuple(rs.rand(3))) for _ in range(10)]
+    palette += [s.lambertian(s.checker(tuple(rs.rand(3)), tuple(rs.rand(3)))) for _ in range(2)]
+    palette += [s.metal(tuple(0.5 + 0.5 * rs.rand(3)), 0.1 * rs.rand()) for _ in range(3)] + [s.dielectric(1.5)]
+    pitch, base = 0.25, 0.2
+    half_x, half_z = 0.5 * nx * pitch, 0.5 * nz * pitch
+    gx, gz = half_x + 8.0, half_z + 8.0
+    s.triangle((-gx, 0, -gz), (-gx, 0, gz), (gx, 0, -gz), ground)
+    s.triangle((gx, 0, gz), (gx, 0, -gz), (-gx, 0, gz), ground)
+    for i in range(nx):
+        for j in range(nz):
+            x, z = f(-half_x + i * pitch), f(-half_z + j * pitch)
+            apex = (x + f(0.5 * base), f(0.15 + 0.25 * rs.rand()), z + f(0.5 * base))
+            c = [(x, 0, z), (x + f(base), 0, z), (x + f(base), 0, z + f(base)), (x, 0, z + f(base))]
+            for k in range(4):
+                s.triangle(c[k], apex, c[(k + 1) % 4], palette[rs.randint(0, len(palette))])
+    s.sphere((-4, 1.6, -1), 1.0, s.lambertian(img))
+    s.sphere((3, 1.3, 0.5), 0.8, s.lambertian(s.image_view(img, 4.0)))
+    s.sphere((0, 2.2, -2), 0.7, s.metal((0.8, 0.8, 0.9), 0.05))
+    s.rect(-half_x, half_x, 0, 3, -half_z - 1.0, s.lambertian(img))
+    return s, _cam(aspect, look_from=(0, 7, 15), look_at=(0, 0.2, 0), vfov=42.0, aperture=0.05, focus=16.0)
+
+
 def cornell(aspect=1.0):
     """BASELINE config 3: Cornell box.  hittable_t has no rotate/translate and only xy_rect at top level
     (render.hpp:22-23), so floor / ceiling / side walls / light are thin boxes and the back wall an xy_rect;
@@ -272,4 +305,5 @@ ALL = {
     "empty": empty, "single_light": single_light, "triangle_mesh": triangle_mesh, "rect_axes": rect_axes,
     "cornell": cornell,
 }
+# (c4_mesh -- 10 000 triangles -- is too slow for the brute-force oracle at whole-image sizes: see test_config4_*)
 REFERENCE_COMPATIBLE = [k for k in ALL if k != "rect_axes"]

@@ -450,3 +450,103 @@ def test_negative_radius_and_nested_spheres(cport):
     want, cnt = cport.render(s, cam, 160, 120, 8, 50)
     assert_parity(got, want, "hollow glass")
     assert st["scans"] == cnt.scans
+
+
+# ---------------------------------------------------------------- flat culling (pt_prims.cuh "FLAT CULLING", BASELINE config 4)
+def _flat_soup(seed, n, with_media):
+    """Rectangles (all three axes), triangles, boxes and a few spheres in random order -- enough of each kind for a
+    tree per kind -- optionally on both sides of constant media."""
+    rs = np.random.RandomState(seed)
+    s = scenes.Scene()
+    mats = [s.lambertian((0.6, 0.5, 0.4)), s.metal((0.8, 0.8, 0.8), 0.1), s.dielectric(1.5), s.lambertian(s.checker((0.1, 0.1, 0.1), (0.9, 0.9, 0.9))),
+            s.lightsource((3, 3, 3))]
+    s.sphere((0, -1000, 0), 1000, mats[0])
+    for i in range(n):
+        k = rs.randint(0, 10)
+        c = np.array([rs.uniform(-5, 5), rs.uniform(0.1, 3.0), rs.uniform(-5, 5)], dtype=np.float32)
+        m = mats[rs.randint(0, 5) if i % 9 == 0 else rs.randint(0, 4)]
+        if k < 5:
+            e = rs.uniform(-0.6, 0.6, (2, 3))
+            s.triangle(c, (c + e[0]).astype(np.float32), (c + e[1]).astype(np.float32), m)
+        elif k < 7:
+            a = rs.uniform(0.1, 0.9, 2)
+            s.rect(c[0], c[0] + a[0], c[1], c[1] + a[1], c[2], m, axis=int(rs.randint(0, 3)) if with_media else abi.AXIS_XY)
+        elif k < 9:
+            s.box(c, (c + rs.uniform(0.1, 0.7, 3)).astype(np.float32), m)
+        else:
+            s.sphere(c, 0.25, m)
+        if with_media and i in (n // 3, 2 * n // 3):
+            s.medium_sphere(c, 1.2, 0.8, (0.9, 0.9, 0.9))
+    cam = scenes.make_camera((11, 4, 9), (0, 1, 0), (0, 1, 0), 35.0, 4 / 3, 0.05, 14.0)
+    return s, cam
+
+
+@pytest.mark.parametrize("with_media", [False, True])
+def test_flat_trees_parity_vs_oracle(cport, with_media):
+    """Trees over rectangles, triangles and boxes; with media the trees behind the first medium are walked
+    sequentially per ray (LATE), and spheres behind a medium force the sequential scan of the whole list."""
+    sc, cam = _flat_soup(21 + with_media, 400, with_media)
+    for (w, h, spp) in ((96, 72, 6), (20, 12, 9)):  # (the small one runs in short rounds from the start)
+        got = R.render(sc, cam, w, h, spp, 50)
+        st = R.stats()
+        want, cnt = cport.render(sc, cam, w, h, spp, 50)
+        assert_parity(got, want, ("flat soup", with_media, w, h))
+        assert st["scans"] == cnt.scans
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("name", ["mesh", "soup", "soup_media"])
+def test_flat_culling_is_invisible(name, kernel):
+    """Box trees and the grazing index are an optimisation only: the same bits with and without them, both kernels."""
+    if name == "mesh":
+        sc, cam = scenes.c4_mesh(4 / 3, nx=30, nz=12)
+    else:
+        sc, cam = _flat_soup(5, 300, name == "soup_media")
+    L = R.lib()
+    try:
+        L.pt_debug_set_kernel(kernel)
+        L.pt_debug_set_cull(0)
+        plain = R.render(sc, cam, 120, 90, 4, 50)
+        scans_plain = R.stats()["scans"]
+        L.pt_debug_set_cull(1)
+        culled = R.render(sc, cam, 120, 90, 4, 50)
+        assert np.array_equal(_bits(plain), _bits(culled)), name
+        assert R.stats()["scans"] == scans_plain
+    finally:
+        L.pt_debug_set_cull(1)
+        L.pt_debug_set_kernel(0)
+
+
+def test_config4_mesh_tiles_at_full_spp(cport):
+    """BASELINE config 4 (10 002 triangles, checker + image textures, 1920x1080, 256 spp, depth 50): tiles of the
+    full-size image at FULL spp with true global seeds against the oracle's brute-force scan."""
+    w, h, spp, d = 1920, 1080, 256, 50
+    sc, cam = scenes.c4_mesh(w / h)
+    assert len(sc.arrays()["triangles"]) == 10002
+    for (x0, y0) in ((950, 420), (300, 560), (1500, 250)):
+        tile = abi.pt_region(x0, y0, 16, 6, 1)
+        got = R.render_region(sc, cam, w, h, spp, d, tile)
+        scans = R.stats()["scans"]
+        want, cnt = cport.render_region(sc, cam, w, h, spp, d, tile)
+        assert_parity(got, want, ("config 4 tile", x0, y0))
+        assert scans == cnt.scans
+
+
+def test_config4_culling_pays(cport):
+    """Config 4 at reduced size: the trees must make the frame at least 10x faster than testing every triangle."""
+    w, h, spp = 480, 270, 2
+    sc, cam = scenes.c4_mesh(w / h)
+    L = R.lib()
+    R.render(sc, cam, w, h, spp, 50)  # warm-up
+    culled = R.render(sc, cam, w, h, spp, 50)
+    ms_culled, scans = R.stats()["kernel_ms"], R.stats()["scans"]
+    try:
+        L.pt_debug_set_cull(0)
+        plain = R.render(sc, cam, w, h, spp, 50)
+        ms_plain = R.stats()["kernel_ms"]
+        assert R.stats()["scans"] == scans
+    finally:
+        L.pt_debug_set_cull(1)
+    assert np.array_equal(_bits(plain), _bits(culled))
+    print("config 4 at %dx%dx%d: %.2f ms with trees, %.2f ms without" % (w, h, spp, ms_culled, ms_plain))
+    assert ms_plain >= 10.0 * ms_culled
