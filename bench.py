@@ -77,7 +77,7 @@ WORKLOADS = {
     "c3": ("Cornell box of thin boxes + xy_rect with two constant_medium smoke boxes and a light, 1024x1024, 1024 spp, "
            "depth 50 (BASELINE config 3)", 3, _tile(128, 96)),
     "c4": ("10 002-triangle pyramid mesh, checker + image textures (numpy-RNG layout), 1920x1080, 256 spp, depth 50 "
-           "(BASELINE config 4)", 3, _tile(128, 64)),
+           "(BASELINE config 4)", 3, _tile(96, 48)),
     "c5": ("4K motion blur + depth of field, 388 moving of 485 spheres (numpy-RNG layout), 3840x2160, 4096 spp, depth 50 "
            "(BASELINE config 5)", 1, _tile(96, 64)),
 }

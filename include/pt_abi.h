@@ -247,6 +247,20 @@ int pt_render_region_device(const pt_device_scene* scene, int width, int height,
                             int depth, const pt_camera* camera, const pt_region* region,
                             float* d_out, int64_t out_row_pitch, void* stream);
 
+/* Progressive rendering (the reference's per-pixel loop state, render.hpp:94-105): trace
+ * samples [spp_from, spp_to) of every pixel of the region.  d_state holds 4 floats per pixel of the region
+ * (state_row_pitch in PIXELS per region row): the running sum r, g, b and the pixel's xorshift32 state (bit
+ * pattern).  It is read when spp_from > 0 and always written; d_out receives sum / spp_to (render.hpp:102), so
+ * that 0..a followed by a..b leaves exactly the framebuffer of one launch 0..b. */
+int pt_render_resume_device(const pt_device_scene* scene, int width, int height, int spp_from, int spp_to,
+                            int depth, const pt_camera* camera, const pt_region* region, float* d_state,
+                            int64_t state_row_pitch, float* d_out, int64_t out_row_pitch, void* stream);
+/* The same with host buffers, blocking: `state` is float[region.h][region.w][4] (in and out), `out` as in
+ * pt_render_region. */
+int pt_render_resume(int width, int height, int spp_from, int spp_to, int depth, const pt_camera* camera,
+                     const pt_scene* hitables, const pt_region* region, float* state, float* out,
+                     int64_t out_row_pitch);
+
 /* Counters accumulated by launches on this device scene since the last reset
  * (paths, scans only; synchronises the device). */
 int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* scans, int reset);

@@ -27,6 +27,9 @@ int pt_oracle_render_region(int width, int height, int spp, int depth, const pt_
                             const pt_scene* scene, const pt_region* region, float* out,
                             int64_t out_row_pitch, int dynamic_schedule, int nthreads,
                             pt_oracle_counters* counters);
+/* The reference's USE_SINGLE_TASK mode (render.hpp:113-122): one RNG stream, default seed, x-major pixel order. */
+int pt_oracle_render_single_task(int width, int height, int spp, int depth, const pt_camera* cam,
+                                 const pt_scene* scene, float* fb, pt_oracle_counters* counters);
 int pt_oracle_max_threads(void);
 void pt_oracle_kat_xorshift(uint32_t seed, int n, uint32_t* out);
 void pt_oracle_kat_float(uint32_t seed, int n, float* out);

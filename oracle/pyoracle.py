@@ -119,6 +119,19 @@ class CPort(_Base):
     def render(self, scene, camera, width, height, spp, depth, **kw):
         return self.render_region(scene, camera, width, height, spp, depth, None, **kw)
 
+    def render_single_task(self, scene, camera, width, height, spp, depth):
+        """The reference's USE_SINGLE_TASK mode (render.hpp:113-122): one RNG stream for the whole image."""
+        self.lib.pt_oracle_render_single_task.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4
+        s, keep = scene.as_c()
+        cam = camera_c(camera)
+        out = np.zeros((height, width, 3), dtype=np.float32)
+        cnt = Counters()
+        rc = self.lib.pt_oracle_render_single_task(width, height, spp, depth, C.addressof(cam), C.addressof(s),
+                                                   out.ctypes.data, C.addressof(cnt))
+        if rc != 0:
+            raise RuntimeError("pt_oracle_render_single_task failed (%d)" % rc)
+        return out, cnt
+
 
 class Ref(_Base):
     """oracle/_ref/libptref.so -- the reference's own code; fixed list of template instantiations."""

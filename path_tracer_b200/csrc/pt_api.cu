@@ -362,10 +362,19 @@ void pt_scene_free(pt_device_scene* s) {
 int pt_render_region_device(const pt_device_scene* cscene, int width, int height, int spp, int depth,
                             const pt_camera* camera, const pt_region* region, float* d_out, int64_t out_row_pitch,
                             void* stream) {
+  return pt_render_resume_device(cscene, width, height, 0, spp, depth, camera, region, nullptr, 0, d_out, out_row_pitch, stream);
+}
+
+int pt_render_resume_device(const pt_device_scene* cscene, int width, int height, int spp_from, int spp, int depth,
+                            const pt_camera* camera, const pt_region* region, float* d_state, int64_t state_row_pitch,
+                            float* d_out, int64_t out_row_pitch, void* stream) {
   pt_device_scene* scene = const_cast<pt_device_scene*>(cscene);
   if (!scene) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render_region_device: null scene");
   const int rc = check_render_args(width, height, spp, camera, region, d_out);
   if (rc != PT_OK) return rc;
+  if (spp_from < 0 || spp_from >= spp) return fail(PT_ERR_INVALID_ARGUMENT, "render: need 0 <= spp_from < spp_to");
+  if (spp_from > 0 && !d_state) return fail(PT_ERR_INVALID_ARGUMENT, "render: resuming needs the per-pixel state");
+  if (d_state && depth <= 0) return fail(PT_ERR_INVALID_ARGUMENT, "render: progressive rendering needs depth > 0");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PT_CUDA(cudaSetDevice(scene->device));
   if (region->w == 0 || region->h == 0) return PT_OK;
@@ -386,6 +395,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   p.region = *region;
   p.out = d_out;
   p.out_row_pitch = out_row_pitch;
+  p.state = d_state, p.state_row_pitch = state_row_pitch, p.spp_from = spp_from;
   p.counters = scene->counters;
   p.team_size = g_team_size_override;  // 0 = chosen from the pixel count at launch
   p.kernel_kind = g_kernel_kind;
@@ -412,7 +422,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   // work), the tiles are sorted by probed cost, and the frame starts with the most expensive tiles so
   // that the deepest pixels have the whole frame to finish and the cheapest ones fill its end.
   const unsigned long long pixels = (unsigned long long)region->w * (unsigned long long)region->h;
-  if (g_lpt_enabled && pixels >= 32768ull && spp >= 8) {
+  if (g_lpt_enabled && pixels >= 32768ull && spp - spp_from >= 8) {
     const int pw = (region->w + kProbeStep - 1) / kProbeStep, ph = (region->h + kProbeStep - 1) / kProbeStep;
     const int tiles_x = (region->w + kTile - 1) / kTile, tiles_y = (region->h + kTile - 1) / kTile;
     const size_t need = (size_t)pw * ph + 2 * (size_t)tiles_x * tiles_y;
@@ -428,7 +438,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
     int* tile_order = probe_cost + (size_t)pw * ph;
     int* scratch = tile_order + (size_t)tiles_x * tiles_y;
     RenderParams probe = p;
-    probe.order_mode = 2, probe.probe_cost = probe_cost, probe.spp = 1, probe.counters = nullptr;
+    probe.order_mode = 2, probe.probe_cost = probe_cost, probe.spp = 1, probe.spp_from = 0, probe.state = nullptr, probe.counters = nullptr;
     probe.kernel_kind = 0;  // the probe always runs on the wavefront kernel
     probe.pixel_counter = next_queue_head();
     probe.heavy.stamp = ++scene->launch_stamp;
@@ -448,7 +458,7 @@ int pt_render_region_device(const pt_device_scene* cscene, int width, int height
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
   scene->kernel_launches += 1;
-  scene->paths_launched += (unsigned long long)region->w * region->h * spp;
+  scene->paths_launched += (unsigned long long)region->w * region->h * (unsigned long long)(spp - spp_from);
   return PT_OK;
 }
 
@@ -613,6 +623,39 @@ int pt_render_region(int width, int height, int spp, int depth, const pt_camera*
   for (auto& x : ev) cudaEventDestroy(x);
   cudaStreamSynchronize(0);
   cached_free(0, d_out, d_out_bytes);
+  pt_scene_free(ds);
+  return rc;
+}
+
+int pt_render_resume(int width, int height, int spp_from, int spp_to, int depth, const pt_camera* camera, const pt_scene* hitables,
+                     const pt_region* region, float* state, float* out, int64_t out_row_pitch) {
+  if (!hitables || !state) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render_resume: null argument");
+  int rc = check_render_args(width, height, spp_to, camera, region, out);
+  if (rc != PT_OK) return rc;
+  if (region->w == 0 || region->h == 0) return PT_OK;
+  pt_device_scene* ds = nullptr;
+  rc = upload(hitables, 0, &ds, nullptr, nullptr);
+  if (rc != PT_OK) return rc;
+  const size_t n_pixels = (size_t)region->w * region->h;
+  float *d_state = nullptr, *d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_state, n_pixels * 7 * sizeof(float));
+  if (e != cudaSuccess) {
+    pt_scene_free(ds);
+    return cuda_fail(e, "cudaMalloc(progressive state)");
+  }
+  d_out = d_state + n_pixels * 4;
+  if (spp_from > 0) e = cudaMemcpy(d_state, state, n_pixels * 4 * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rc = pt_render_resume_device(ds, width, height, spp_from, spp_to, depth, camera, region, d_state, region->w, d_out,
+                                 (int64_t)region->w * 3, nullptr);
+    if (rc == PT_OK) e = cudaMemcpy(state, d_state, n_pixels * 4 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (rc == PT_OK && e == cudaSuccess)
+      e = cudaMemcpy2D(out, out_row_pitch * sizeof(float), d_out, (size_t)region->w * 3 * sizeof(float), (size_t)region->w * 3 * sizeof(float),
+                       region->h, cudaMemcpyDeviceToHost);
+  }
+  if (rc == PT_OK && e != cudaSuccess) rc = cuda_fail(e, "pt_render_resume");
+  if (rc == PT_OK) rc = pt_scene_read_counters(ds, nullptr, nullptr, 0);
+  cudaFree(d_state);
   pt_scene_free(ds);
   return rc;
 }

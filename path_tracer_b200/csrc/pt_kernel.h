@@ -40,6 +40,11 @@ struct RenderParams {
   pt_region region;
   float* out;               // device (or peer-mapped) pointer
   long long out_row_pitch;  // floats
+  // progressive rendering (pt_render_resume*): this launch traces samples [spp_from, spp) of every pixel; the per-pixel
+  // state {sum r, g, b, RNG bits} is read when spp_from > 0 and written back when `state` is set
+  float* state;             // 4 floats per pixel of the region, or null
+  long long state_row_pitch;  // pixels
+  int spp_from;
   unsigned long long* pixel_counter;  // work-queue heads ([0] everybody's, [1] the express CTAs'), zeroed before launch
   unsigned long long express_positions;  // leading queue positions reserved for the express CTAs (set by the launcher)
   unsigned long long* counters;       // [0] += closest-hit scans (may be null)

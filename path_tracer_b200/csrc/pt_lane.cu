@@ -34,6 +34,7 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
   bool exhausted_queue = false;       // the pixel queue has run dry
   int px = 0, py = 0;                 // global pixel coordinates
   float* out_px = nullptr;
+  float* state_px = nullptr;
   int sample = p.spp;
   int bounce = 0;
   Rng rng { 0u };
@@ -62,6 +63,9 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
         unsigned long long optr = (unsigned long long)out_px;
         PT_MOVE(optr);
         out_px = (float*)optr;
+        optr = (unsigned long long)state_px;
+        PT_MOVE(optr);
+        state_px = (float*)optr;
         int np = need_path ? 1 : 0;
         PT_MOVE(np);
         need_path = np != 0;
@@ -76,8 +80,7 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
     // ---- (A) path regeneration: render.hpp:94-105 sample loop, :130-133 seeding
     if (need_path && live && sample == p.spp) {
       // final_color /= samples; fb[y][x] = final_color (render.hpp:102-105); one writer per team
-      const V3 fin = vdivs(acc, fspp);
-      if (member == 0) out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+      if (member == 0) pixel_finish(p, out_px, state_px, acc, rng, fspp);
       live = false;
     }
     {
@@ -86,18 +89,15 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
         unsigned long long idx = 0ull;
         if (wants && member == 0) {  // the team leader pulls the next pixel (skipping tile positions outside the region)
           int tx, ty;
-          float* tp;
+          float *tp, *ts;
           do idx = atomicAdd(p.pixel_counter, 1ull);
-          while (idx < p.n_positions && !queue_pixel(p, idx, tx, ty, tp));
+          while (idx < p.n_positions && !queue_pixel(p, idx, tx, ty, tp, ts));
         }
         idx = __shfl_sync(0xffffffffu, idx, lane - member);
         if (wants) {
           if (idx < p.n_positions) {
-            queue_pixel(p, idx, px, py, out_px);
-            // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
-            rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
-            acc = v3(0.f, 0.f, 0.f);
-            sample = 0;
+            queue_pixel(p, idx, px, py, out_px, state_px);
+            pixel_start(p, px, py, state_px, rng, acc, sample);
             pix_scans = 0;
             live = true;
           } else {
@@ -135,7 +135,7 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
     // A warp that finds itself holding one of the image's deepest pixels stops taking new pixels: as its
     // other pixels finish it is re-packed into ever larger teams, until all 32 lanes scan for the deep
     // pixel and its remaining thousands of bounces take microseconds each instead of a full round.
-    if (__any_sync(0xffffffffu, live && pix_scans > kDeepBase + kDeepRate * sample)) exhausted_queue = true;
+    if (__any_sync(0xffffffffu, live && pix_scans > kDeepBase + kDeepRate * (sample - p.spp_from))) exhausted_queue = true;
   }
 
 }

@@ -471,7 +471,11 @@ PT_DEV void scan_flat_range(const Keys& sc, const float4* __restrict__ data, int
     }
   }
 }
+#ifdef PT_NO_FLAT_TREES
+PT_DEV bool has_tree(const SceneDesc&, const Group&) { return false; }
+#else
 PT_DEV bool has_tree(const SceneDesc& sc, const Group& g) { return g.tree >= 0 && sc.flat_cull != 0u; }
+#endif
 PT_DEV const float4* flat_data(const SceneView& sv, int type) {
   return type == G_RECT ? sv.rect : type == G_TRIANGLE ? sv.triangle : sv.box;
 }

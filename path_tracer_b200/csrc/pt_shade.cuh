@@ -227,7 +227,27 @@ PT_DEV bool shade(const SceneDesc& sc, const SceneView& sv, int depth, bool smem
 //                 deep pixels of the image start at once, the cheapest ones fill the end of the frame)
 //   order_mode 0  consecutive positions spread over the image by a multiplicative permutation
 //   order_mode 2  the cost probe itself: every kProbeStep-th pixel of every kProbeStep-th row
-PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, int& py, float*& out_px) {
+// A pixel's first sample of this launch: the seed of render.hpp:130-133 and an empty sum, or -- resuming -- the state
+// an earlier launch left (sum and RNG after spp_from samples).
+PT_DEV void pixel_start(const RenderParams& p, int px, int py, const float* state_px, Rng& rng, V3& acc, int& sample) {
+  // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
+  rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
+  acc = v3(0.f, 0.f, 0.f);
+  sample = 0;
+  if (p.order_mode == 2) {
+    rng.s = (rng.s * 2654435761u) | 1u;  // cost probe: a throw-away stream, never the pixel's
+  } else if (state_px && p.spp_from > 0) {
+    const float4 s = *reinterpret_cast<const float4*>(state_px);
+    acc = v3(s.x, s.y, s.z), rng.s = __float_as_uint(s.w), sample = p.spp_from;
+  }
+}
+// The pixel is finished for this launch: render.hpp:102-105, and the state for a later pt_render_resume.
+PT_DEV void pixel_finish(const RenderParams& p, float* out_px, float* state_px, V3 acc, Rng rng, float fspp) {
+  const V3 fin = vdivs(acc, fspp);
+  out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+  if (state_px) *reinterpret_cast<float4*>(state_px) = make_float4(acc.x, acc.y, acc.z, __uint_as_float(rng.s));
+}
+PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, int& py, float*& out_px, float*& state_px) {
   unsigned long long k, xx;
   if (p.order_mode == 1) {
     const int tile = p.tile_order[pos / (unsigned long long)(kTile * kTile)];
@@ -246,6 +266,7 @@ PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, 
   px = p.region.x0 + (int)xx;
   py = p.region.y0 + (int)k * p.region.y_stride;
   out_px = p.out + (long long)k * p.out_row_pitch + 3ll * (long long)xx;
+  state_px = p.state ? p.state + 4ll * ((long long)k * p.state_row_pitch + (long long)xx) : nullptr;
   return true;
 }
 

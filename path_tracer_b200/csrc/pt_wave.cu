@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
   // The first p.express_positions positions of the queue (the most expensive tiles of the LPT order) belong to the
   // express CTAs, which trace them in short rounds from the start; everybody else begins behind them.
-  auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py) -> bool {
+  auto next_pixel = [&](uint32_t& pixq, Rng& rng, int& px, int& py, V3& acc0, int& sample0) -> bool {
     for (;;) {
       if (*reinterpret_cast<volatile int*>(&W.pixel_dry)) return false;  // (a set-once flag; a stale 0 only costs one more atomic)
       unsigned long long pos;
@@ -320,12 +320,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           return false;
         }
       }
-      float* unused;
-      if (!queue_pixel(p, pos, px, py, unused)) continue;  // a tile position outside the region
+      float *unused, *state_px;
+      if (!queue_pixel(p, pos, px, py, unused, state_px)) continue;  // a tile position outside the region
       pixq = (uint32_t)pos;
-      // std::hash<size_t> is the identity; LocalPseudoRNG takes a uint32_t (rtweekend.hpp:35)
-      rng.s = (uint32_t)((unsigned long long)py * (unsigned long long)p.width + (unsigned long long)px);
-      if (p.order_mode == 2) rng.s = (rng.s * 2654435761u) | 1u;  // cost probe: a throw-away stream, never the pixel's
+      pixel_start(p, px, py, state_px, rng, acc0, sample0);
       return true;
     }
   };
@@ -491,7 +489,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   if (tid < 8) W.counts[tid] = 0;
   if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.n_items_f = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
+#ifdef PT_NO_FLAT_TREES  // (experiments only: what do the tree paths cost the scenes that have none?)
+  cap_s = W.cap_s, cap_m = W.cap_m, cap_f = 0, n_tgroups = 0;
+#else
   cap_s = W.cap_s, cap_m = W.cap_m, cap_f = W.cap_f, n_tgroups = W.n_tgroups;
+#endif
   if (!express) {  // (an express CTA goes straight to the hand-off service, whose first source is its reserved tiles)
     // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
     const int cap = p.pool_cap;
@@ -501,11 +503,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       if (slot < cap) {
         uint32_t pixq;
         Rng rng;
-        int px, py;
-        if (next_pixel(pixq, rng, px, py)) {
+        int px, py, sample0;
+        V3 acc0;
+        if (next_pixel(pixq, rng, px, py, acc0, sample0)) {
           Ray ray;
           camera_ray(cam, px, py, fwidth, fheight, rng, ray);
-          store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+          store_ray(slot, ray, v3(1.f, 1.f, 1.f), acc0, rng, 0, sample0);
           W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;  // (an express CTA never hands a pixel off)
           alive = true;
         }
@@ -529,12 +532,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           // it serves from the start, whenever it has room
           uint32_t pixq;
           Rng rng;
-          int px, py;
-          if (express && next_pixel(pixq, rng, px, py)) {
+          int px, py, sample0;
+          V3 acc0;
+          if (express && next_pixel(pixq, rng, px, py, acc0, sample0)) {
             const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
             Ray ray;
             camera_ray(cam, px, py, fwidth, fheight, rng, ray);
-            store_ray(slot, ray, v3(1.f, 1.f, 1.f), v3(0.f, 0.f, 0.f), rng, 0, 0);
+            store_ray(slot, ray, v3(1.f, 1.f, 1.f), acc0, rng, 0, sample0);
             W.pix[slot] = pixq, W.scans[slot] = -1;  // (never handed off again)
             W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
           } else {
@@ -860,15 +864,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           // the path ended: render.hpp:100-105
           acc = vadd(acc, contribution);
           int px, py;
-          float* out_px;
-          queue_pixel(p, pixq, px, py, out_px);
+          float *out_px, *state_px;
+          queue_pixel(p, pixq, px, py, out_px, state_px);
           if (++sample == p.spp) {
-            if (p.order_mode == 2) {
+            if (p.order_mode == 2)
               p.probe_cost[pixq] = scans;  // cost probe: how deep did one sample of this pixel go
-            } else {
-              const V3 fin = vdivs(acc, fspp);
-              out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
-            }
+            else
+              pixel_finish(p, out_px, state_px, acc, rng, fspp);
             new_pixel = true;
           } else {
             camera_ray(cam, px, py, fwidth, fheight, rng, ray);
@@ -877,7 +879,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           }
         }
         // a heavy pixel leaves for a CTA that runs short rounds, with its complete state
-        if (!new_pixel && own && p.order_mode != 2 && scans > kHeavyBase + heavy_rate * sample) {
+        if (!new_pixel && own && p.order_mode != 2 && scans > kHeavyBase + heavy_rate * (sample - p.spp_from)) {
           unsigned int i = 0u;
           if (reserve_heavy(i)) {
             float* q = hq.entries + (size_t)(i & (hq.cap - 1u)) * kHeavyEntryWords;
@@ -897,12 +899,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         if (new_pixel) {
           if (!own && p.counters) atomicMax(p.counters + 14, (unsigned long long)(-1 - scans));  // stats: longest stay in the service
           int px, py;
-          alive = mode == 0 && next_pixel(pixq, rng, px, py);
+          alive = mode == 0 && next_pixel(pixq, rng, px, py, acc, sample);
           if (alive) {
             camera_ray(cam, px, py, fwidth, fheight, rng, ray);
             att = v3(1.f, 1.f, 1.f);
-            acc = v3(0.f, 0.f, 0.f);
-            bounce = 0, sample = 0;
+            bounce = 0;
             W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;
             own = !express;
           } else if (mode == 1) {
@@ -1045,8 +1046,13 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     // COOPERATIVE launch: the CTAs wait for each other (the service loop ends when every CTA has reported), so the grid
     // must be co-resident; launched this way the runtime guarantees it -- or fails the launch -- whatever else is
     // running on the device (another stream's render, another process).
+#ifdef PT_NO_COOP  // (experiments only)
+    kernel<<<grid, kWaveThreads, dyn, stream>>>(q);
+    return cudaGetLastError();
+#else
     void* args[] = { (void*)&q };
     return cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)grid), dim3((unsigned)kWaveThreads), args, dyn, stream);
+#endif
   }
   return launch_lane(p, device, grid_override, stream, info);
 }

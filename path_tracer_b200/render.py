@@ -45,6 +45,8 @@ def lib():
         L.pt_scene_free.argtypes = [C.c_void_p]
         L.pt_scene_free.restype = None
         L.pt_render_region_device.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
+        L.pt_render_resume_device.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+        L.pt_render_resume.argtypes = [C.c_int] * 5 + [C.c_void_p] * 5 + [C.c_int64]
         L.pt_scene_read_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.pt_scene_launch_count.argtypes = [C.c_void_p, C.c_void_p]
         L.pt_get_stats.argtypes = [C.c_void_p]
@@ -99,6 +101,21 @@ def render_region(scene, camera, width, height, spp, depth, region):
     _check(lib().pt_render_region(width, height, spp, depth, C.addressof(cam), C.addressof(s), C.addressof(region),
                                   out.ctypes.data, region.w * 3))
     return out
+
+
+def render_resume(scene, camera, width, height, spp_from, spp_to, depth, region, state=None):
+    """Progressive rendering through pt_render_resume: samples [spp_from, spp_to) of every pixel of `region`.
+    -> (framebuffer = sum / spp_to, state [region.h, region.w, 4] to pass to the next call)."""
+    s, keep = scene.as_c()
+    cam = camera_c(camera)
+    if state is None:
+        assert spp_from == 0
+        state = np.zeros((region.h, region.w, 4), dtype=np.float32)
+    state = np.ascontiguousarray(state, dtype=np.float32).copy()
+    out = np.zeros((region.h, region.w, 3), dtype=np.float32)
+    _check(lib().pt_render_resume(width, height, spp_from, spp_to, depth, C.addressof(cam), C.addressof(s), C.addressof(region),
+                                  state.ctypes.data, out.ctypes.data, region.w * 3))
+    return out, state
 
 
 class DeviceScene:

@@ -550,3 +550,33 @@ def test_config4_culling_pays(cport):
     assert np.array_equal(_bits(plain), _bits(culled))
     print("config 4 at %dx%dx%d: %.2f ms with trees, %.2f ms without" % (w, h, spp, ms_culled, ms_plain))
     assert ms_plain >= 10.0 * ms_culled
+
+
+# ---------------------------------------------------------------- progressive rendering
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_resume_is_bit_identical_to_one_launch(c1, kernel):
+    """render.hpp:94-105 keeps {RNG, sum} per pixel across its sample loop: samples 0..40 followed by 40..100 from the
+    saved state must leave exactly the framebuffer (and the state) of one launch 0..100."""
+    sc, cam, (w, h, _, d) = c1
+    region = abi.pt_region(300, 200, 96, 40, 1)
+    L = R.lib()
+    try:
+        L.pt_debug_set_kernel(kernel)
+        whole = R.render_region(sc, cam, w, h, 100, d, region)
+        fb_a, st_a = R.render_resume(sc, cam, w, h, 0, 40, d, region)
+        assert np.array_equal(_bits(fb_a), _bits(R.render_region(sc, cam, w, h, 40, d, region)))
+        fb_b, st_b = R.render_resume(sc, cam, w, h, 40, 100, d, region, st_a)
+        assert np.array_equal(_bits(fb_b), _bits(whole))
+        fb_c, st_c = R.render_resume(sc, cam, w, h, 0, 100, d, region)
+        assert np.array_equal(_bits(st_c), _bits(st_b)) and np.array_equal(_bits(fb_c), _bits(whole))
+        # three uneven steps, the LPT order on in one of them (>= 32768 pixels and >= 8 samples) and off in the others
+        big = abi.pt_region(0, 100, 800, 48, 1)
+        one = R.render_region(sc, cam, w, h, 12, d, big)
+        fb, st = R.render_resume(sc, cam, w, h, 0, 1, d, big)
+        fb, st = R.render_resume(sc, cam, w, h, 1, 10, d, big, st)
+        fb, st = R.render_resume(sc, cam, w, h, 10, 12, d, big, st)
+        assert np.array_equal(_bits(fb), _bits(one))
+    finally:
+        L.pt_debug_set_kernel(0)
+    with pytest.raises(R.PathTracerError):
+        R.render_resume(sc, cam, w, h, 5, 5, d, region, st_a)
