@@ -52,6 +52,7 @@ struct RenderParams {
   int kernel_kind;                    // 0 = wavefront kernel (default), 1 = lane kernel
   int pool_cap;                       // wavefront kernel: pixels a CTA may hold (set by the launcher)
   unsigned int staged_bytes;          // wavefront kernel: bytes of the arena kept in shared memory (set by the launcher)
+  unsigned int tree_list_bytes;       // wavefront kernel: dynamic shared memory behind them for the tree lists (set by the launcher)
   int n_express;                      // wavefront kernel: CTAs that only serve the hand-off queue (< 0 = automatic)
   // pixel order of the wavefront kernel (queue position -> pixel)
   int order_mode;                     // 0 = scrambled, 1 = tiles in `tile_order` (heaviest first), 2 = cost probe grid

@@ -471,13 +471,9 @@ PT_DEV void scan_flat_range(const Keys& sc, const float4* __restrict__ data, int
     }
   }
 }
-#ifdef PT_NO_FLAT_TREES
-PT_DEV bool has_tree(const SceneDesc&, const Group&) { return false; }
-#else
 PT_DEV bool has_tree(const SceneDesc& sc, const Group& g) { return g.tree >= 0 && sc.flat_cull != 0u; }
-#endif
 PT_DEV const float4* flat_data(const SceneView& sv, int type) {
-  return type == G_RECT ? sv.rect : type == G_TRIANGLE ? sv.triangle : sv.box;
+  return type == G_RECT ? sv.rect() : type == G_TRIANGLE ? sv.triangle() : sv.box();
 }
 template <bool kSmem>
 PT_DEV void scan_flat_group(const SceneDesc& sc, const SceneView& sv, const Group& g, const Ray& r, int first, int step,
@@ -570,18 +566,20 @@ template <bool kSmem> PT_DEV uint32_t graze_node_bits(const float4* __restrict__
   return (mn <= taud && mx >= -taud) ? 0x80000000u : 0u;
 }
 
-// Visit the leaves of a tree whose ancestors (and whose own box) all pass `test` (sign bit of its result).
+// Level l of a tree by name, not by index (a dynamically indexed struct would live in local memory).
+PT_DEV int tree_off(const Tree& t, int l) { return l == 0 ? t.off[0] : l == 1 ? t.off[1] : t.off[2]; }
+PT_DEV int tree_n(const Tree& t, int l) { return l == 0 ? t.n[0] : l == 1 ? t.n[1] : t.n[2]; }
+// Visit the leaves under the nodes [first, first + count) of level `top` whose ancestors below `top` (and whose own
+// box) all pass `test` (sign bit of its result).  The whole tree: top = t.levels - 1, first = 0, count = n[top].
 template <typename Test, typename Leaf>
-PT_DEV void tree_walk(const Tree& t, const float4* __restrict__ nodes, Test test, Leaf leaf) {
-  // levels by name, not by index (a dynamically indexed struct would live in local memory): A = the top list, B = its
-  // children, C = theirs
-  const int top = t.levels - 1;
-  const int off_a = top == 0 ? t.off[0] : top == 1 ? t.off[1] : t.off[2], n_a = top == 0 ? t.n[0] : top == 1 ? t.n[1] : t.n[2];
+PT_DEV void tree_walk(const Tree& t, const float4* __restrict__ nodes, int top, int first, int count, Test test, Leaf leaf) {
+  // A = the nodes of level `top`, B = their children, C = theirs
+  const int off_a = tree_off(t, top);
   const int off_b = top == 2 ? t.off[1] : t.off[0], n_b = top == 2 ? t.n[1] : t.n[0];
   const float4* b2 = nodes + off_a;
-  const int n2 = n_a;
+  const int n2 = first + count;
 #pragma unroll 1
-  for (int c2 = 0; c2 < n2; c2 += 32) {
+  for (int c2 = first; c2 < n2; c2 += 32) {
     const int k2 = min(32, n2 - c2);
     uint32_t m2 = 0;
 #pragma unroll 1
@@ -649,14 +647,14 @@ struct FlatTrees {
   float extent;
 };
 PT_DEV FlatTrees flat_trees(const SceneDesc& sc, const SceneView& sv, int type) {
-  return FlatTrees { flat_data(sv, type), sv.trees, sv.nodes, sv.tree_ids, sc.flat_extent };
+  return FlatTrees { flat_data(sv, type), sv.trees(), sv.nodes(), sv.tree_ids(), sc.flat_extent };
 }
 template <bool kSmem>
 __device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, Ray r, int first, int step, Best best) {
   const FlatRay fr = make_flat_ray(ft.extent, r);
   const Tree t = ft.trees[g.tree];
   tree_walk(
-      t, ft.nodes, [&](const float4* box) { return flat_node_bits<kSmem>(box, fr, r, best.t); },
+      t, ft.nodes, t.levels - 1, 0, tree_n(t, t.levels - 1), [&](const float4* box) { return flat_node_bits<kSmem>(box, fr, r, best.t); },
       [&](int leaf) {
         const int b = g.begin + leaf * kFlatChunk;
         scan_flat_range<kSmem>(sc, ft.data, g.type, b + first, min(b + kFlatChunk, g.begin + g.count), step, r, best);
@@ -664,7 +662,7 @@ __device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, 
   if (g.gtree >= 0 && fr.ok) {
     const Tree gt = ft.trees[g.gtree];
     tree_walk(
-        gt, ft.nodes, [&](const float4* box) { return graze_node_bits<kSmem>(box, r.d, fr.taud); },
+        gt, ft.nodes, gt.levels - 1, 0, tree_n(gt, gt.levels - 1), [&](const float4* box) { return graze_node_bits<kSmem>(box, r.d, fr.taud); },
         [&](int leaf) { scan_graze_leaf<kSmem>(sc, ft.data, ft.ids + gt.leaf_ids + leaf * kFlatChunk, first, step, r, fr.taud, best); });
   }
   return best;
@@ -673,26 +671,26 @@ __device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, 
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
 // of each group.  `act`: this lane's team carries a real ray (the others ride along so that the
 // warp stays converged on the shared loads and the shuffles).
-template <bool kSmem>
+template <bool kSmem, bool kTrees = true>
 PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, bool act, int member,
                         int team_size) {
   Best best { kInf, -1 };
   const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant
   CullRay cr;
   const int cull_set = make_cull_ray(sc, r, cr);
-  const float4* sphere_boxes = sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
-  const float4* moving_boxes = sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks;
+  const float4* sphere_boxes = sv.sphere_box() + cull_set * 2 * (int)sc.n_sphere_chunks;
+  const float4* moving_boxes = sv.moving_box() + cull_set * 2 * (int)sc.n_moving_chunks;
   const int n_groups = (int)sc.n_groups;
   for (int gi = 0; gi < n_groups; ++gi) {
-    const Group g = sv.groups[gi];
+    const Group g = sv.groups()[gi];
     const int end = g.begin + g.count;
     switch (g.type) {
       case G_SPHERE:
-        scan_spheres<kSmem, false>(sc, sv.sphere, sphere_boxes, sc.sphere_aux, g.begin, end, team_size, r, a, 0.f, cr, act,
+        scan_spheres<kSmem, false>(sc, sv.sphere(), sphere_boxes, sc.sphere_aux, g.begin, end, team_size, r, a, 0.f, cr, act,
                                    G_SPHERE, best);
         break;
       case G_MOVING_SPHERE:
-        scan_spheres<kSmem, true>(sc, sv.moving, moving_boxes, sc.moving_aux, g.begin, end, team_size, r, a,
+        scan_spheres<kSmem, true>(sc, sv.moving(), moving_boxes, sc.moving_aux, g.begin, end, team_size, r, a,
                                   fdiv(fsub(r.tm, g.time0), g.den), cr, act, G_MOVING_SPHERE, best);
         break;
       case G_MEDIUM: {
@@ -707,7 +705,7 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       }
       default:
         if (act) {
-          if (has_tree(sc, g))
+          if (kTrees && has_tree(sc, g))
             best = scan_flat_tree<kSmem>(key_table(sc), flat_trees(sc, sv, g.type), g, r, member, team_size, best);
           else
             scan_flat_group<kSmem>(sc, sv, g, r, g.begin + member, team_size, best);

@@ -77,12 +77,12 @@ PT_DEV int build_record(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       V3 center;
       const SphereAux* aux;
       if (type == G_SPHERE) {
-        const float4 s = smem ? sv.sphere[sphere_slot(idx)] : __ldg(sv.sphere + sphere_slot(idx));
+        const float4 s = smem ? sv.sphere()[sphere_slot(idx)] : __ldg(sv.sphere() + sphere_slot(idx));
         center = v3(s.x, s.y, s.z);
         aux = sc.sphere_aux + idx;
       } else {
-        const float4 s = smem ? sv.moving[moving_slot(idx)] : __ldg(sv.moving + moving_slot(idx));
-        const float4 v = smem ? sv.moving[moving_slot(idx) + 2 * kSphereChunk] : __ldg(sv.moving + moving_slot(idx) + 2 * kSphereChunk);
+        const float4 s = smem ? sv.moving()[moving_slot(idx)] : __ldg(sv.moving() + moving_slot(idx));
+        const float4 v = smem ? sv.moving()[moving_slot(idx) + 2 * kSphereChunk] : __ldg(sv.moving() + moving_slot(idx) + 2 * kSphereChunk);
         aux = sc.moving_aux + idx;
         center = moving_center(v3(s.x, s.y, s.z), v3(v.x, v.y, v.z), fdiv(fsub(r.tm, aux->time0), aux->den));
       }
@@ -92,8 +92,8 @@ PT_DEV int build_record(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       return aux->material;
     }
     case G_RECT: {  // rectangle.hpp:42-47
-      const float4 q0 = smem ? sv.rect[2 * idx] : __ldg(sv.rect + 2 * idx);
-      const float4 q1 = smem ? sv.rect[2 * idx + 1] : __ldg(sv.rect + 2 * idx + 1);
+      const float4 q0 = smem ? sv.rect()[2 * idx] : __ldg(sv.rect() + 2 * idx);
+      const float4 q1 = smem ? sv.rect()[2 * idx + 1] : __ldg(sv.rect() + 2 * idx + 1);
       const int axis = __float_as_int(q1.y);
       const AxisSel s = axis_select(r, axis);
       const float a = fadd(s.oa, fmul(best.t, s.da));
@@ -110,8 +110,8 @@ PT_DEV int build_record(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
       return aux->material;
     }
     case G_BOX: {  // box.hpp:29-50: replay the six sides to find the winning one
-      const float4 p0 = smem ? sv.box[2 * idx] : __ldg(sv.box + 2 * idx);
-      const float4 p1 = smem ? sv.box[2 * idx + 1] : __ldg(sv.box + 2 * idx + 1);
+      const float4 p0 = smem ? sv.box()[2 * idx] : __ldg(sv.box() + 2 * idx);
+      const float4 p1 = smem ? sv.box()[2 * idx + 1] : __ldg(sv.box() + 2 * idx + 1);
       float t, a, b;
       const V3 lo = v3(p0.x, p0.y, p0.z), hi = v3(p1.x, p1.y, p1.z);
       const int side = box_hit_t(r, lo, hi, kTMin, kInf, t, a, b);

@@ -53,35 +53,26 @@ PT_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- scene view
+// The kernels' view of the scan blob (in shared or global memory): nothing but the blob's base and the descriptor
+// that holds the offsets -- the arrays' addresses are formed where they are used (one load of the offset, which the
+// compiler hoists out of the loops) instead of living in a dozen 64-bit registers across the whole kernel.
 struct SceneView {
-  const Group* groups;
-  const float4* sphere;
-  const float4* moving;
-  const float4* rect;
-  const float4* triangle;
-  const float4* box;
-  const float4* sphere_box;  // chunk boxes, set 0 first
-  const float4* moving_box;
-  const Tree* trees;         // flat groups' box trees and grazing indices (pt_packed.h)
-  const float4* nodes;       // their boxes
-  const float4* tree_ids;    // grazing index: the leaves' {g, triangle} lists
+  const unsigned char* base;
+  const SceneDesc* sc;
+  template <typename T> PT_DEV const T* at(uint32_t off) const { return reinterpret_cast<const T*>(base + off); }
+  PT_DEV const Group* groups() const { return at<Group>(sc->off_groups); }
+  PT_DEV const float4* sphere() const { return at<float4>(sc->off_sphere); }
+  PT_DEV const float4* moving() const { return at<float4>(sc->off_moving); }
+  PT_DEV const float4* rect() const { return at<float4>(sc->off_rect); }
+  PT_DEV const float4* triangle() const { return at<float4>(sc->off_triangle); }
+  PT_DEV const float4* box() const { return at<float4>(sc->off_box); }
+  PT_DEV const float4* sphere_box() const { return at<float4>(sc->off_sphere_box); }  // chunk boxes, set 0 first
+  PT_DEV const float4* moving_box() const { return at<float4>(sc->off_moving_box); }
+  PT_DEV const Tree* trees() const { return at<Tree>(sc->off_trees); }          // flat groups' box trees and grazing indices
+  PT_DEV const float4* nodes() const { return at<float4>(sc->off_nodes); }      // their boxes
+  PT_DEV const float4* tree_ids() const { return at<float4>(sc->off_tree_ids); }  // grazing index: the leaves' {g, triangle} lists
 };
-// Point the view at the scan blob (in shared or global memory).
-PT_DEV SceneView scene_view(const SceneDesc& sc, const unsigned char* blob_base) {
-  SceneView sv;
-  sv.groups = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
-  sv.sphere = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
-  sv.moving = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
-  sv.rect = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
-  sv.triangle = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
-  sv.box = reinterpret_cast<const float4*>(blob_base + sc.off_box);
-  sv.sphere_box = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
-  sv.moving_box = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
-  sv.trees = reinterpret_cast<const Tree*>(blob_base + sc.off_trees);
-  sv.nodes = reinterpret_cast<const float4*>(blob_base + sc.off_nodes);
-  sv.tree_ids = reinterpret_cast<const float4*>(blob_base + sc.off_tree_ids);
-  return sv;
-}
+PT_DEV SceneView scene_view(const SceneDesc& sc, const unsigned char* blob_base) { return SceneView { blob_base, &sc }; }
 
 template <bool kSmem> PT_DEV float4 ld4(const float4* p) {
   if constexpr (kSmem)

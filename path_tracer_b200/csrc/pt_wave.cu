@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "pt_abi.h"
 #include "pt_device.cuh"
 #include "pt_kernel.h"
@@ -134,10 +136,10 @@ struct WavePool {
   int n_next;      // length of list_a being built
   int n_own;       // of those, pixels this CTA pulled from the pixel queue itself
   int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
-  int n_items_f;   // (ray, leaf) items of the flat groups with a tree
-  int cap_s, cap_m, cap_f;  // shares of the item list: static items from the front, flat items behind them, moving ones from the back
-  int n_tgroups;   // flat groups with a tree in front of the first constant_medium (traversed per ray in BOXES)
+  int n_tgroups;   // flat groups with a tree in front of the first constant_medium (expanded breadth first: wave_tree_expand)
   int tgroups[kMaxTreeGroups];
+  int tree_passes; // tree passes per round: the deepest of those trees has this many levels above its leaves
+  int tl_n[3], tl_off[3], tl_cap[3];  // the tree lists (in dynamic shared memory behind the staged scene): node items of pass 0 and 1, leaf items
   int free_count;
   int pixel_dry;   // the pixel queue has run dry
   int service;     // hand-off service: 0 = keep polling, 1 = every producer is done and the queue is empty
@@ -207,43 +209,70 @@ __device__ __noinline__ void wave_run_flat(WavePool* W, KeyTable kt, FlatTrees f
   flat_item_scan<kSmem>(kt, ft, g, it.y, ray, first, step, b);
   if (b.id >= 0) atomicMin(&W->best64[slot], pack_winner(b.t, key_of(kt, b.id)));
 }
-// BOXES for one ray and one flat group with a tree: every leaf whose (grown) box the ray crosses, and every leaf of
-// the grazing index that may hold a triangle the ray grazes, becomes an item; what does not fit into the group's
-// share of the item list is scanned in place and folded into the ray's winner `v`.  Out of line: the hot loops of
-// the sphere path must own the instruction cache and the registers.
+// TREE EXPANSION (BOXES and the tree passes): test the nodes [first, first + count) of level `level` of one tree of
+// one flat group against one ray.  A crossed leaf becomes a (ray, leaf) item for ITEMS, a crossed inner node a (ray,
+// node) item for the next tree pass -- the trees are walked BREADTH FIRST, one level per pass, every pass a flat list of
+// items of the same size spread over the whole CTA, like the (ray, chunk) items of the spheres: a depth-first walk
+// per ray leaves the lanes of a warp in loops of different lengths (measured on the 10 002-triangle mesh: 9.8 of 32
+// lanes busy, and the CTA waiting at the barrier for its deepest walk).  What does not fit a list is walked depth
+// first here and now, and folded into the ray's winner `v`.  Out of line: the hot loops of the sphere path must own
+// the instruction cache and the registers.
+//   node item  {slot | tree group << 10 | grazing index << 13 | level << 14, node}
+//   leaf item  {slot | tree group << 10, leaf | grazing index << 31}
 template <bool kSmem>
-__device__ __noinline__ unsigned long long wave_emit_flat(WavePool* W, KeyTable kt, FlatTrees ft, Group g, uint32_t slot_tg, Ray ray,
-                                                          int item_base, int cap_f, unsigned long long* counters,
-                                                          unsigned long long v) {
+__device__ __noinline__ unsigned long long wave_tree_expand(WavePool* W, uint2* lists, KeyTable kt, FlatTrees ft, Group g, uint32_t slot_tg,
+                                                            uint32_t graze, int level, int first, int count, int out_list, Ray ray,
+                                                            unsigned long long* counters, unsigned long long v) {
   const FlatRay fr = make_flat_ray(ft.extent, ray);
-  auto emit = [&](int leaf, uint32_t graze) {
-    const uint2 it = make_uint2(slot_tg, (uint32_t)leaf | (graze << 31));
-    const int at = atomicAdd(&W->n_items_f, 1);
-    if (at < cap_f) {
-      W->items[item_base + at] = it;
-    } else {
-      if (counters) atomicAdd(counters + 15, 1ull);  // stats: items scanned in place
-      Best b { kInf, -1 };
-      flat_item_scan<kSmem>(kt, ft, g, it.y, ray, 0, 1, b);
-      if (b.id >= 0) {
-        const unsigned long long w64 = pack_winner(b.t, key_of(kt, b.id));
-        if (w64 < v) v = w64;
-      }
+  if (graze && !fr.ok) return v;  // (a ray that is not culled visits every leaf of the box tree already)
+  const Tree t = ft.trees[graze ? g.gtree : g.tree];
+  const float4* boxes = ft.nodes + tree_off(t, level);
+  auto test = [&](const float4* box) {
+    return graze ? graze_node_bits<kSmem>(box, ray.d, fr.taud) : flat_node_bits<kSmem>(box, fr, ray, kInf);
+  };
+  auto leaf_here = [&](int leaf) {  // overflow: the leaf's elements, in place
+    if (counters) atomicAdd(counters + 15, 1ull);  // stats: items scanned in place
+    Best b { kInf, -1 };
+    flat_item_scan<kSmem>(kt, ft, g, (uint32_t)leaf | (graze << 31), ray, 0, 1, b);
+    if (b.id >= 0) {
+      const unsigned long long w64 = pack_winner(b.t, key_of(kt, b.id));
+      if (w64 < v) v = w64;
     }
   };
-  const Tree t = ft.trees[g.tree];
-  tree_walk(
-      t, ft.nodes, [&](const float4* box) { return flat_node_bits<kSmem>(box, fr, ray, kInf); }, [&](int leaf) { emit(leaf, 0u); });
-  if (g.gtree >= 0 && fr.ok) {
-    const Tree gt = ft.trees[g.gtree];
-    tree_walk(
-        gt, ft.nodes, [&](const float4* box) { return graze_node_bits<kSmem>(box, ray.d, fr.taud); }, [&](int leaf) { emit(leaf, 1u); });
+  const int dest = level == 0 ? 2 : out_list;
+#pragma unroll 1
+  for (int c = first; c < first + count; c += 32) {
+    const int k = min(32, first + count - c);
+    uint32_t m = 0;
+#pragma unroll 1
+    for (int j = 0; j < k; ++j) m = __funnelshift_l(test(boxes + 2 * (c + j)), m, 1);
+    if (m == 0u) continue;
+    int at = atomicAdd(&W->tl_n[dest], __popc(m));
+#pragma unroll 1
+    while (m) {
+      const int top = 31 - __clz((int)m);
+      m &= ~(1u << top);
+      const int node = c + (k - 1 - top);
+      if (at < W->tl_cap[dest]) {
+        lists[W->tl_off[dest] + at] = level == 0 ? make_uint2(slot_tg, (uint32_t)node | (graze << 31))
+                                                 : make_uint2(slot_tg | (graze << 13) | ((uint32_t)level << 14), (uint32_t)node);
+      } else if (level == 0) {
+        leaf_here(node);
+      } else {
+        const int c0 = node * kTreeFan;
+        tree_walk(t, ft.nodes, level - 1, c0, min(kTreeFan, tree_n(t, level - 1) - c0), test, leaf_here);
+      }
+      ++at;
+    }
   }
   return v;
 }
 }  // namespace
 
-template <bool kSmem>
+// kTrees = false: the scene has no flat group with a tree (or culling is off) -- the tree paths are compiled out, so
+// that scenes without them (spheres and a handful of flats: the default scene) keep their registers and their
+// instruction-cache footprint.
+template <bool kSmem, bool kTrees>
 __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wave_kernel(const RenderParams p) {
   extern __shared__ __align__(16) unsigned char smem_blob[];
   __shared__ __align__(8) uint64_t stage_bar;
@@ -298,7 +327,6 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   const int n_groups = (int)sc.n_groups;
   unsigned int n_scans = 0;
 
-  int cap_s = 0, cap_m = 0, cap_f = 0, n_tgroups = 0;  // shares of the item list, flat groups with a tree (set once the tables exist)
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
   // The first p.express_positions positions of the queue (the most expensive tiles of the LPT order) belong to the
   // express CTAs, which trace them in short rounds from the start; everybody else begins behind them.
@@ -334,6 +362,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   // Claim the next entry: its position (read it, then release_heavy()), or false when there is none right now.
   auto take_heavy = [&](unsigned int& pos_out) -> bool {
     unsigned int pos = ld_volatile_u32(hq.ctrl + 0);
+    if (pos == ld_volatile_u32(hq.ctrl + 1)) return false;  // empty (the common answer: two independent loads, one round trip)
     for (int attempt = 0; attempt < 8; ++attempt) {
       const int dif = (int)(ld_volatile_u32(hq.ready + (pos & (hq.cap - 1u))) - (pos + 1u));
       if (dif == 0) {
@@ -418,35 +447,56 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       const int top = 31 - __clz((int)hits);
       hits &= ~(1u << top);
       const int chunk = cb + (nb - 1 - top);
-      if (at < (moving ? cap_m : cap_s)) {
+      if (at < (moving ? kWaveItemsMoving : kWaveItemsStatic)) {
         W.items[moving ? kWaveItems - 1 - at : at] = make_uint2((uint32_t)slot | ((uint32_t)chunk << 10), __float_as_uint(f));
       } else {
         if (p.counters) atomicAdd(p.counters + 15, 1ull);  // stats: items scanned in place (tests check that it happens)
         if (moving)
-          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
+          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving(), sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
         else
-          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
+          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere(), sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
       }
       ++at;
     }
   };
 
   // (ray, leaf) items of the flat groups with a tree: flat_item_scan / wave_emit_flat above the kernel
+  uint2* const tree_lists = reinterpret_cast<uint2*>(smem_stage + ((staged + 15u) & ~15u));
   auto run_flat_item = [&](const uint2 it, int first, int step) {
-    const Group g = sv.groups[W.tgroups[it.x >> 10]];
+    const Group g = sv.groups()[W.tgroups[(it.x >> 10) & 7u]];
     wave_run_flat<kSmem>(&W, key_table(sc), flat_trees(sc, sv, g.type), g, it, first, step);
   };
+  // BOXES: the top level of both trees (boxes, grazing index) of one flat group for one ray
   auto emit_flat_items = [&](int slot, const Ray& ray, int tg, unsigned long long& v) {
-    const Group g = sv.groups[W.tgroups[tg]];
-    v = wave_emit_flat<kSmem>(&W, key_table(sc), flat_trees(sc, sv, g.type), g, (uint32_t)slot | ((uint32_t)tg << 10), ray, cap_s, cap_f,
-                              p.counters, v);
+    const Group g = sv.groups()[W.tgroups[tg]];
+    const uint32_t slot_tg = (uint32_t)slot | ((uint32_t)tg << 10);
+    const FlatTrees ft = flat_trees(sc, sv, g.type);
+    const Tree t = ft.trees[g.tree];
+    v = wave_tree_expand<kSmem>(&W, tree_lists, key_table(sc), ft, g, slot_tg, 0u, t.levels - 1, 0, tree_n(t, t.levels - 1), 0, ray, p.counters, v);
+    if (g.gtree >= 0) {
+      const Tree gt = ft.trees[g.gtree];
+      v = wave_tree_expand<kSmem>(&W, tree_lists, key_table(sc), ft, g, slot_tg, 1u, gt.levels - 1, 0, tree_n(gt, gt.levels - 1), 0, ray, p.counters, v);
+    }
+  };
+  // a tree pass: the children of one (ray, node) item
+  auto expand_node_item = [&](const uint2 it, int pass) {
+    const int slot = (int)(it.x & 1023u);
+    const Group g = sv.groups()[W.tgroups[(it.x >> 10) & 7u]];
+    const uint32_t graze = (it.x >> 13) & 1u;
+    const int level = (int)(it.x >> 14);
+    const FlatTrees ft = flat_trees(sc, sv, g.type);
+    const Tree t = ft.trees[graze ? g.gtree : g.tree];
+    const int c0 = (int)it.y * kTreeFan;
+    const unsigned long long v = wave_tree_expand<kSmem>(&W, tree_lists, key_table(sc), ft, g, it.x & 0x1fffu, graze, level - 1, c0,
+                                                         min(kTreeFan, tree_n(t, level - 1) - c0), pass + 1, load_ray(slot), p.counters, kNoHit64);
+    if (v != kNoHit64) atomicMin(&W.best64[slot], v);
   };
 
   int mode = 0;  // 0: this CTA's share of the pixel queue (none for an express CTA); 1: hand-off service
   if (tid == 0) {
     int nb = 0;
     for (int gi = 0; gi < n_groups && nb >= 0; ++gi) {
-      const Group g = sv.groups[gi];
+      const Group g = sv.groups()[gi];
       if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
       const int c_end = (g.begin + g.count) / kSphereChunk;
       for (int cb = g.begin / kSphereChunk; cb < c_end; cb += kFineBoxes) {
@@ -461,9 +511,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     // the flat objects in front of the first medium (as many as fit; the rest stays with the sequential part)
     int nf = 0, nt = 0, late = n_groups;
     for (int gi = 0; gi < n_groups; ++gi) {
-      const Group g = sv.groups[gi];
+      const Group g = sv.groups()[gi];
       const bool flat = g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX;
-      const bool tree = flat && has_tree(sc, g);
+      const bool tree = kTrees && flat && has_tree(sc, g);
       if (g.type == G_MEDIUM || (flat && !tree && nf + 6 * g.count > kMaxFlats) || (tree && nt == kMaxTreeGroups)) {
         late = gi;
         break;
@@ -479,21 +529,23 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           for (int side = 0; side < 6; ++side) W.flats[nf++] = make_int2(G_BOX | (side << 8), g.begin + i);
     }
     W.n_flats = nf, W.first_late_group = late, W.n_tgroups = nt;
-    // shares of the item list (the split of a sphere-only scene is the one measured best on the default scene)
-    const bool has_s = sc.n_sphere_chunks != 0u, has_m = sc.n_moving_chunks != 0u;
-    const int for_spheres = nt == 0 ? kWaveItems : (has_s || has_m) ? kWaveItems / 2 : 0;
-    W.cap_f = kWaveItems - for_spheres;
-    W.cap_s = nt == 0 ? kWaveItemsStatic : has_m ? (has_s ? for_spheres * 3 / 8 : 0) : for_spheres;
-    W.cap_m = for_spheres - W.cap_s;
+    // the tree lists share what the launch left of the dynamic shared memory: node items of pass 0 / pass 1 / leaf items
+    int passes = 0;
+    for (int k = 0; k < nt; ++k) {
+      const Group g = sv.groups()[W.tgroups[k]];
+      passes = max(passes, sv.trees()[g.tree].levels - 1);
+      if (g.gtree >= 0) passes = max(passes, sv.trees()[g.gtree].levels - 1);
+    }
+    W.tree_passes = passes;
+    const int cap = (int)(p.tree_list_bytes / sizeof(uint2));
+    const int c0 = passes >= 1 ? cap / (passes == 1 ? 3 : 4) : 0, c1 = passes >= 2 ? cap / 4 : 0;
+    W.tl_off[0] = 0, W.tl_cap[0] = c0, W.tl_off[1] = c0, W.tl_cap[1] = c1, W.tl_off[2] = c0 + c1, W.tl_cap[2] = cap - c0 - c1;
+    W.tl_n[0] = W.tl_n[1] = W.tl_n[2] = 0;
   }
   if (tid < 8) W.counts[tid] = 0;
-  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.n_items_f = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
+  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
   __syncthreads();
-#ifdef PT_NO_FLAT_TREES  // (experiments only: what do the tree paths cost the scenes that have none?)
-  cap_s = W.cap_s, cap_m = W.cap_m, cap_f = 0, n_tgroups = 0;
-#else
-  cap_s = W.cap_s, cap_m = W.cap_m, cap_f = W.cap_f, n_tgroups = W.n_tgroups;
-#endif
+
   if (!express) {  // (an express CTA goes straight to the hand-off service, whose first source is its reserved tiles)
     // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
     const int cap = p.pool_cap;
@@ -590,12 +642,18 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       __nanosleep(300);
       continue;  // (the next write of W.service is behind the barrier at the loop top)
     }
+    const int n_tgroups = kTrees ? W.n_tgroups : 0;  // flat groups with a tree in front of the first medium
     const int units_per_ray = W.n_blocks + n_tgroups;  // short rounds: a ray's sphere chunks in blocks, its flat trees one by one
     const bool fine = n <= kFineRays && W.blocks_ok && units_per_ray > 0;
 #ifdef PT_PHASE_TIMING
+#ifdef PT_PHASE_EXPRESS_ONLY  // time the express CTAs' short rounds only (the frame's critical path)
+#define PT_PHASE_WHO (express && mode == 1)
+#else
+#define PT_PHASE_WHO true
+#endif
     long long pt_t0 = clock64();
 #define PT_PHASE(k)                                                                                   \
-  if (tid == 0 && p.counters) {                                                                       \
+  if (tid == 0 && p.counters && PT_PHASE_WHO) {                                                                       \
     const long long now = clock64();                                                                  \
     atomicAdd(p.counters + 16 + (k), (unsigned long long)(now - pt_t0));                              \
     pt_t0 = now;                                                                                      \
@@ -611,7 +669,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int slot = (int)W.list_a[e];
         const Ray ray = load_ray(slot);
         Rng rng { W.rng[slot] };
-        const Best best = closest_hit<kSmem>(sc, sv, ray, rng, true, 0, 1);
+        const Best best = closest_hit<kSmem, kTrees>(sc, sv, ray, rng, true, 0, 1);
         W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
         W.rng[slot] = rng.s;  // a constant_medium may have drawn from it (constant_medium.hpp:65)
       }
@@ -628,18 +686,18 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         Best inl { kInf, -1 };
         unsigned long long v = kNoHit64;
         const int unit = fine ? w - e * units_per_ray : 0;
-        if (fine && unit >= W.n_blocks) {  // short rounds: one flat tree of the ray
+        if (kTrees && fine && unit >= W.n_blocks) {  // short rounds: one flat tree of the ray
           emit_flat_items(slot, ray, unit - W.n_blocks, v);
           if (v != kNoHit64) atomicMin(&W.best64[slot], v);
           continue;
         }
         const int4 blk = fine ? W.blocks[unit] : make_int4(0, 0, 0, 0);
         for (int gi = fine ? blk.x : 0; gi < (fine ? blk.x + 1 : n_groups); ++gi) {
-          const Group g = sv.groups[gi];
+          const Group g = sv.groups()[gi];
           if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
           const bool moving = g.type == G_MOVING_SPHERE;
-          const float4* boxes = moving ? sv.moving_box + cull_set * 2 * (int)sc.n_moving_chunks
-                                       : sv.sphere_box + cull_set * 2 * (int)sc.n_sphere_chunks;
+          const float4* boxes = moving ? sv.moving_box() + cull_set * 2 * (int)sc.n_moving_chunks
+                                       : sv.sphere_box() + cull_set * 2 * (int)sc.n_sphere_chunks;
           const float f = moving ? fdiv(fsub(ray.tm, g.time0), g.den) : 0.f;
           // the group's outsized spheres (a ground sphere ...) are tested right here, one by one: their chunks are never
           // culled and mostly padding (the same sphere for every lane: broadcast loads)
@@ -650,13 +708,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             for (int i = g.begin; i < g.begin + g.n_open; ++i) {
               float cx, cy, cz, r2f;
               if (moving) {
-                const float4* ps = sv.moving + moving_slot(i);
+                const float4* ps = sv.moving() + moving_slot(i);
                 if ((int)sphere_filter_bits<kSmem, true>(ps, f, ray, af) < 0) {
                   sphere_center<kSmem, true>(ps, f, cx, cy, cz, r2f);
                   sphere_roots_scan(sc, inl, ray, a, cx, cy, cz, exact_r2(sc.moving_aux, i), make_id(G_MOVING_SPHERE, i));
                 }
               } else {
-                const float4* ps = sv.sphere + sphere_slot(i);
+                const float4* ps = sv.sphere() + sphere_slot(i);
                 if ((int)sphere_filter_bits<kSmem, false>(ps, f, ray, af) < 0) {
                   sphere_center<kSmem, false>(ps, f, cx, cy, cz, r2f);
                   sphere_roots_scan(sc, inl, ray, a, cx, cy, cz, exact_r2(sc.sphere_aux, i), make_id(G_SPHERE, i));
@@ -686,8 +744,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           // (ray, object) in SPHERES)
           Best fb { kInf, -1 };
           for (int gi = 0; gi < W.first_late_group; ++gi) {
-            const Group g = sv.groups[gi];
-            if ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && !has_tree(sc, g)) scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, fb);
+            const Group g = sv.groups()[gi];
+            if ((g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) && !(kTrees && has_tree(sc, g))) scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, fb);
           }
           if (fb.id >= 0) {
             const unsigned long long w64 = pack_winner(fb.t, key_of(sc, fb.id));
@@ -700,11 +758,21 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
     }
     __syncthreads();
+    if (kTrees && !sequential_scan) {
+      // ---- TREE PASSES: one level of the flat groups' trees per pass, one thread per (ray, node) item
+      for (int pass = 0; pass < W.tree_passes; ++pass) {
+        const int n_items = min(W.tl_n[pass], W.tl_cap[pass]);
+        const uint2* const items = tree_lists + W.tl_off[pass];
+        for (int i = tid; i < n_items; i += kWaveThreads) expand_node_item(items[i], pass);
+        __syncthreads();
+      }
+    }
     PT_PHASE(0)
 
     // ---- SPHERES: one thread per (ray, chunk) item, or per quarter of one
     if (!sequential_scan) {
-      const int n_s = min(W.n_items_s, cap_s), n_m = min(W.n_items_m, cap_m), n_f = min(W.n_items_f, cap_f);
+      const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving), n_f = kTrees ? min(W.tl_n[2], W.tl_cap[2]) : 0;
+      const uint2* const leaf_items = tree_lists + W.tl_off[2];
 #ifdef PT_PHASE_TIMING
       if (tid == 0 && p.counters) atomicAdd(p.counters + 23, (unsigned long long)(n_s + n_m));
 #endif
@@ -715,8 +783,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int fl_base = (m_base + n_m + 31) & ~31;  // (ray, leaf) items of the flat trees: one thread per leaf
         for (int i = tid; i < fl_base + n_f; i += kWaveThreads) {
           if ((i >= n_s && i < m_base) || (i >= m_base + n_m && i < fl_base)) continue;
-          if (i >= fl_base) {
-            run_flat_item(W.items[cap_s + (i - fl_base)], 0, 1);
+          if (kTrees && i >= fl_base) {
+            run_flat_item(leaf_items[i - fl_base], 0, 1);
             continue;
           }
           const bool moving = i >= m_base;
@@ -726,10 +794,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           const float a = vdot(ray.d, ray.d);
           Best b { kInf, -1 };
           if (moving)
-            scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+            scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving(), sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
                                                      __uint_as_float(it.y), G_MOVING_SPHERE, b);
           else
-            scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
+            scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere(), sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
                                                       G_SPHERE, b);
           if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
         }
@@ -744,8 +812,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int n_flats = W.n_flats;
         const int fl_base = (f_base + n * n_flats + 31) & ~31;  // flat-tree items: one thread per (leaf, element)
         for (int w = tid; w < fl_base + kFlatChunk * n_f; w += kWaveThreads) {
-          if (w >= fl_base) {
-            run_flat_item(W.items[cap_s + (w - fl_base) / kFlatChunk], (w - fl_base) % kFlatChunk, kFlatChunk);
+          if (kTrees && w >= fl_base) {
+            run_flat_item(leaf_items[(w - fl_base) / kFlatChunk], (w - fl_base) % kFlatChunk, kFlatChunk);
           } else if (w < n_quarters) {
             const int i = w / kParts;
             const bool moving = i >= n_s;
@@ -755,10 +823,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             const float a = vdot(ray.d, ray.d);
             Best b { kInf, -1 };
             if (moving)
-              scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving, sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+              scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving(), sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
                                                             __uint_as_float(it.y), G_MOVING_SPHERE, b);
             else
-              scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere, sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+              scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere(), sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
                                                              0.f, G_SPHERE, b);
             if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
           } else if (w >= f_base && w < f_base + n * n_flats) {
@@ -768,8 +836,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             const Ray ray = load_ray(slot);
             Best b { kInf, -1 };
             if ((fo.x & 255) == G_BOX) {
-              const float4 p0 = ld4<kSmem>(sv.box + 2 * fo.y);
-              const float4 p1 = ld4<kSmem>(sv.box + 2 * fo.y + 1);
+              const float4 p0 = ld4<kSmem>(sv.box() + 2 * fo.y);
+              const float4 p1 = ld4<kSmem>(sv.box() + 2 * fo.y + 1);
               float t, ra, rb;
               if (box_side_hit_t(ray, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), fo.x >> 8, kTMin, kInf, t, ra, rb))
                 b.t = t, b.id = make_id(G_BOX, fo.y);
@@ -787,7 +855,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     PT_PHASE(1)
 
     // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
-    if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.n_items_f = 0;  // (SHADE builds the next round's list)
+    if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.tl_n[0] = 0, W.tl_n[1] = 0, W.tl_n[2] = 0;  // (SHADE builds the next round's list)
     for (int e = tid; e < n; e += kWaveThreads) {
       const int slot = (int)W.list_a[e];
       Best best;
@@ -802,9 +870,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           const Ray ray = load_ray(slot);
           Rng rng { W.rng[slot] };
           for (int gi = late; gi < n_groups; ++gi) {
-            const Group g = sv.groups[gi];
+            const Group g = sv.groups()[gi];
             if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) {
-              if (has_tree(sc, g))
+              if (kTrees && has_tree(sc, g))
                 best = scan_flat_tree<kSmem>(key_table(sc), flat_trees(sc, sv, g.type), g, ray, 0, 1, best);
               else
                 scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, best);
@@ -918,7 +986,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     if (tid < 8) W.counts[tid] = 0;  // (everybody has read them; LATE of the next round is two barriers away)
     PT_PHASE(4)
 #ifdef PT_PHASE_TIMING
-    if (tid == 0 && p.counters) atomicAdd(p.counters + 21, 1ull), atomicAdd(p.counters + 22, (unsigned long long)n);
+    if (tid == 0 && p.counters && PT_PHASE_WHO) atomicAdd(p.counters + 21, 1ull), atomicAdd(p.counters + 22, (unsigned long long)n);
 #endif
   }
 
@@ -986,15 +1054,20 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
   if (p.kernel_kind == 0) {
     // ---- wavefront kernel: one CTA per SM, ray pool + (when it fits) the scan blob in shared memory
     // shared memory: the ray pool, and in front of it the scan blob with the side tables (else the blob alone, else nothing)
-    const size_t pool_bytes = sizeof(WavePool);
-    auto with_pool = [&](size_t bytes) { return (pool_bytes + 127u) / 128u * 128u + bytes; };
-    const long long most = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc);
-    q.staged_bytes = (long long)with_pool(p.scene.stage_bytes) <= most  ? p.scene.stage_bytes
-                     : (long long)with_pool(p.scene.blob_bytes) <= most ? p.scene.blob_bytes
-                                                                        : 0u;
+    // and behind them, for scenes with flat trees, the lists of the breadth-first tree passes (at least kMinTreeListBytes:
+    // a scene is only staged if it leaves that much)
+    const size_t pool_bytes = (sizeof(WavePool) + 127u) / 128u * 128u;
+    const bool trees = p.scene.n_trees != 0u && p.scene.flat_cull != 0u;
+    constexpr long long kMinTreeListBytes = 64 << 10, kMaxTreeListBytes = 128 << 10;
+    const long long room = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc) - (long long)pool_bytes;
+    const long long for_scene = room - (trees ? kMinTreeListBytes : 0);
+    q.staged_bytes = (long long)p.scene.stage_bytes <= for_scene ? p.scene.stage_bytes : (long long)p.scene.blob_bytes <= for_scene ? p.scene.blob_bytes : 0u;
+    const size_t staged_al = ((size_t)q.staged_bytes + 15u) & ~(size_t)15u;
+    q.tree_list_bytes = trees ? (unsigned int)(std::min<long long>(room - (long long)staged_al, kMaxTreeListBytes) & ~15ll) : 0u;
     const bool smem = q.staged_bytes != 0u;
-    const size_t dyn = smem ? with_pool(q.staged_bytes) : pool_bytes;
-    auto kernel = smem ? render_wave_kernel<true> : render_wave_kernel<false>;
+    const size_t dyn = pool_bytes + staged_al + q.tree_list_bytes;
+    auto kernel = smem ? (trees ? render_wave_kernel<true, true> : render_wave_kernel<true, false>)
+                       : (trees ? render_wave_kernel<false, true> : render_wave_kernel<false, false>);
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (err != cudaSuccess) return err;
     // every CTA must be resident at once: the express warps wait for all CTAs to report
