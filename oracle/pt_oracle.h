@@ -35,6 +35,8 @@ void pt_oracle_kat_xorshift(uint32_t seed, int n, uint32_t* out);
 void pt_oracle_kat_float(uint32_t seed, int n, float* out);
 void pt_oracle_kat_vec(uint32_t seed, int kind, int n, float* out);
 void pt_oracle_kat_get_ray(const pt_camera* cam, uint32_t seed, int n, const float* st, float* out);
+int pt_oracle_hit_world_batch(const pt_scene* scene, int n, const float* rays7, const uint32_t* seeds, float* out_t,
+                              int32_t* out_index, uint32_t* out_rng);
 int pt_oracle_kat_hit_scatter(const pt_scene* scene, const float* ray7, uint32_t seed, float* out);
 #ifdef __cplusplus
 }

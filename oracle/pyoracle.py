@@ -119,6 +119,20 @@ class CPort(_Base):
     def render(self, scene, camera, width, height, spp, depth, **kw):
         return self.render_region(scene, camera, width, height, spp, depth, None, **kw)
 
+    def hit_world_batch(self, scene, rays7, seeds):
+        """hit_world (render.hpp:30-51) per ray -> (t [n] float32, vector index of the hit object or -1, generator after)."""
+        self.lib.pt_oracle_hit_world_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        s, keep = scene.as_c()
+        rays7 = np.ascontiguousarray(rays7, dtype=np.float32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = rays7.shape[0]
+        t, idx, rng = np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros(n, np.uint32)
+        rc = self.lib.pt_oracle_hit_world_batch(C.addressof(s), n, rays7.ctypes.data, seeds.ctypes.data, t.ctypes.data, idx.ctypes.data,
+                                                rng.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("pt_oracle_hit_world_batch failed (%d)" % rc)
+        return t, idx, rng
+
     def render_single_task(self, scene, camera, width, height, spp, depth):
         """The reference's USE_SINGLE_TASK mode (render.hpp:113-122): one RNG stream for the whole image."""
         self.lib.pt_oracle_render_single_task.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4

@@ -29,6 +29,7 @@ int g_cull_enabled = 1;
 int g_lpt_enabled = 1;  // pt_debug_set_lpt
 int g_n_express = -1;   // < 0: automatic (pt_debug_set_express)
 int g_kernel_kind = 0;  // 0 = wavefront kernel, 1 = lane kernel (pt_debug_set_kernel)
+int g_fb_stage_enabled = 1;  // pt_debug_set_fb_stage: 0 = scalar stores straight into the caller's framebuffer
 pt_stats g_stats {};
 
 int fail(int code, const std::string& msg) {
@@ -69,6 +70,9 @@ struct pt_device_scene {
   unsigned int launch_stamp = 0;
   int* lpt_buf = nullptr;  // probe costs + tile order + scratch of the LPT pixel ordering
   size_t lpt_ints = 0;
+  FrameTuning* last_tuning = nullptr;  // device: what the last cost probe said (pt_debug_frame_tuning)
+  float* fb_stage = nullptr;  // float4 staging image of the last region size (pt_kernel.h: launch_resolve_fb)
+  size_t fb_stage_bytes = 0;
   int next_slot = 0;
   unsigned int kernel_launches = 0;  // kernels launched since creation (probe, tile sort, render)
   unsigned long long paths_launched = 0;
@@ -163,31 +167,10 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   const size_t o_taux = place(host, ps.tri_aux);
   const size_t o_baux = place(host, ps.box_aux);
   const size_t o_media = place(host, ps.media);
-  std::vector<int32_t> keys;
+  std::vector<int32_t> keys, object_id;
   uint32_t key_base[6];
-  key_base[G_SPHERE] = (uint32_t)keys.size();
-  for (const auto& a : ps.sphere_aux) keys.push_back(a.key);
-  key_base[G_MOVING_SPHERE] = (uint32_t)keys.size();
-  for (const auto& a : ps.moving_aux) keys.push_back(a.key);
-  key_base[G_RECT] = (uint32_t)keys.size();
-  for (const auto& a : ps.rect_aux) keys.push_back(a.key);
-  key_base[G_TRIANGLE] = (uint32_t)keys.size();
-  for (const auto& a : ps.tri_aux) keys.push_back(a.key);
-  key_base[G_BOX] = (uint32_t)keys.size();
-  for (const auto& a : ps.box_aux) keys.push_back(a.key);
-  key_base[G_MEDIUM] = (uint32_t)keys.size();
-  for (const auto& a : ps.media) keys.push_back(a.key);
+  build_key_tables(ps, keys, key_base, object_id);
   const size_t o_keys = place(host, keys);
-  // original object index -> scan id (a sphere's key is -1 - index, any other object's is the index, pt_packed.h)
-  std::vector<int32_t> object_id(std::max<uint32_t>(ps.n_objects, 1u), -1);
-  for (size_t i = 0; i < ps.rect_aux.size(); ++i) object_id[(size_t)ps.rect_aux[i].key] = make_id(G_RECT, (int)i);
-  for (size_t i = 0; i < ps.tri_aux.size(); ++i) object_id[(size_t)ps.tri_aux[i].key] = make_id(G_TRIANGLE, (int)i);
-  for (size_t i = 0; i < ps.box_aux.size(); ++i) object_id[(size_t)ps.box_aux[i].key] = make_id(G_BOX, (int)i);
-  for (size_t i = 0; i < ps.media.size(); ++i) object_id[(size_t)ps.media[i].key] = make_id(G_MEDIUM, (int)i);
-  for (size_t i = 0; i < ps.sphere_aux.size(); ++i)
-    if (ps.sphere_aux[i].material >= 0) object_id[(size_t)(-1 - ps.sphere_aux[i].key)] = make_id(G_SPHERE, (int)i);
-  for (size_t i = 0; i < ps.moving_aux.size(); ++i)
-    if (ps.moving_aux[i].material >= 0) object_id[(size_t)(-1 - ps.moving_aux[i].key)] = make_id(G_MOVING_SPHERE, (int)i);
   const size_t o_objid = place(host, object_id);
   const size_t o_mat = place(host, ps.materials);
   const size_t stage_end = align_up(host.size(), 16);  // what the wavefront kernel keeps in shared memory if it fits
@@ -356,6 +339,7 @@ void pt_scene_free(pt_device_scene* s) {
   cudaDeviceSynchronize();  // nothing may still be using the arena when it is handed to the next upload
   cached_free(s->device, s->arena, s->arena_bytes);
   cached_free(s->device, s->lpt_buf, s->lpt_ints * sizeof(int));
+  cached_free(s->device, s->fb_stage, s->fb_stage_bytes);
   delete s;
 }
 
@@ -395,6 +379,24 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   p.region = *region;
   p.out = d_out;
   p.out_row_pitch = out_row_pitch;
+  p.out_pixel_floats = 3;
+  // Vectorised framebuffer stores: finished pixels go to a float4 staging image with one 16-byte store each, and a
+  // resolve pass packs them into the caller's rows with coalesced 16-byte stores.  Needs 16-byte aligned rows of a
+  // multiple of 4 pixels; anything else keeps the scalar stores.
+  const bool staged_fb = g_fb_stage_enabled && region->w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
+                         (out_row_pitch * (long long)sizeof(float)) % 16 == 0;
+  if (staged_fb) {
+    const size_t need = (size_t)region->w * region->h * 4 * sizeof(float);
+    if (need > scene->fb_stage_bytes) {
+      cached_free(scene->device, scene->fb_stage, scene->fb_stage_bytes);
+      scene->fb_stage = nullptr, scene->fb_stage_bytes = 0;
+      void* buf = nullptr;
+      size_t got = 0;
+      PT_CUDA(cached_malloc(scene->device, &buf, need, &got));
+      scene->fb_stage = static_cast<float*>(buf), scene->fb_stage_bytes = got;
+    }
+    p.out = scene->fb_stage, p.out_row_pitch = 4ll * region->w, p.out_pixel_floats = 4;
+  }
   p.state = d_state, p.state_row_pitch = state_row_pitch, p.spp_from = spp_from;
   p.counters = scene->counters;
   p.team_size = g_team_size_override;  // 0 = chosen from the pixel count at launch
@@ -402,6 +404,7 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   p.pool_cap = 0;
   p.scramble = 1;
   p.n_express = g_n_express;
+  p.tuning = nullptr;
   p.express_positions = 0;
   p.order_mode = 0, p.tile_order = nullptr, p.tiles_x = p.tiles_y = 0, p.probe_cost = nullptr, p.n_positions = 0;
   p.heavy.ctrl = scene->heavy_ctrl, p.heavy.ready = scene->heavy_ready, p.heavy.entries = scene->heavy_entries;
@@ -425,7 +428,7 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   if (g_lpt_enabled && pixels >= 32768ull && spp - spp_from >= 8) {
     const int pw = (region->w + kProbeStep - 1) / kProbeStep, ph = (region->h + kProbeStep - 1) / kProbeStep;
     const int tiles_x = (region->w + kTile - 1) / kTile, tiles_y = (region->h + kTile - 1) / kTile;
-    const size_t need = (size_t)pw * ph + 2 * (size_t)tiles_x * tiles_y;
+    const size_t need = (size_t)pw * ph + 2 * (size_t)tiles_x * tiles_y + sizeof(FrameTuning) / sizeof(int);
     if (need > scene->lpt_ints) {
       cached_free(scene->device, scene->lpt_buf, scene->lpt_ints * sizeof(int));
       scene->lpt_buf = nullptr, scene->lpt_ints = 0;
@@ -437,6 +440,7 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
     int* probe_cost = scene->lpt_buf;
     int* tile_order = probe_cost + (size_t)pw * ph;
     int* scratch = tile_order + (size_t)tiles_x * tiles_y;
+    FrameTuning* tuning = reinterpret_cast<FrameTuning*>(scratch + (size_t)tiles_x * tiles_y);
     RenderParams probe = p;
     probe.order_mode = 2, probe.probe_cost = probe_cost, probe.spp = 1, probe.spp_from = 0, probe.state = nullptr, probe.counters = nullptr;
     probe.kernel_kind = 0;  // the probe always runs on the wavefront kernel
@@ -446,9 +450,12 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
     PT_CUDA(cudaMemsetAsync(probe.pixel_counter, 0, 2 * sizeof(unsigned long long), st));
     cudaError_t pe = launch_render(probe, scene->device, 0, st, nullptr);
     if (pe != cudaSuccess) return cuda_fail(pe, "cost probe launch");
-    pe = launch_tile_order(probe_cost, region->w, region->h, tiles_x, tiles_y, tile_order, scratch, st);
+    pe = launch_tile_order(probe_cost, region->w, region->h, tiles_x, tiles_y, tile_order, scratch, tuning, wave_grid(scene->device),
+                           g_n_express, st);
     if (pe != cudaSuccess) return cuda_fail(pe, "tile order launch");
     p.order_mode = 1, p.tile_order = tile_order, p.tiles_x = tiles_x, p.tiles_y = tiles_y;
+    p.tuning = g_kernel_kind == 0 ? tuning : nullptr;
+    scene->last_tuning = tuning;
     scene->kernel_launches += 2;
   }
   p.pixel_counter = next_queue_head();
@@ -458,6 +465,11 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   cudaError_t e = launch_render(p, scene->device, 0, st, &scene->last_launch);
   if (e != cudaSuccess) return cuda_fail(e, "render kernel launch");
   scene->kernel_launches += 1;
+  if (staged_fb) {
+    e = launch_resolve_fb(scene->fb_stage, region->w, region->h, d_out, out_row_pitch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "framebuffer resolve launch");
+    scene->kernel_launches += 1;
+  }
   scene->paths_launched += (unsigned long long)region->w * region->h * (unsigned long long)(spp - spp_from);
   return PT_OK;
 }
@@ -522,6 +534,56 @@ int pt_debug_set_team_size(int t) {
 // Debug aid (not part of pt_abi.h): 0 = wavefront kernel (default), 1 = lane kernel.
 int pt_debug_set_kernel(int kind) {
   g_kernel_kind = kind;
+  return PT_OK;
+}
+
+// Test hook (not part of pt_abi.h): the closest-hit scan of n host rays {o, d, time} with generator states `seeds`
+// (pt_kernel.h: launch_probe_rays); the chunk boxes are those of `camera`'s shutter interval.
+int pt_debug_closest_hit(pt_device_scene* scene, const pt_camera* camera, int n, const float* rays7, const uint32_t* seeds, int mode,
+                         float* out_t, int32_t* out_index, uint32_t* out_rng) {
+  if (!scene || !camera || n < 0 || (n && (!rays7 || !seeds || !out_t || !out_index || !out_rng)))
+    return fail(PT_ERR_INVALID_ARGUMENT, "pt_debug_closest_hit: bad argument");
+  if (n == 0) return PT_OK;
+  PT_CUDA(cudaSetDevice(scene->device));
+  const int crc = update_chunk_boxes(scene, camera, nullptr);
+  if (crc != PT_OK) return crc;
+  unsigned char* buf = nullptr;
+  const size_t nn = (size_t)n;
+  PT_CUDA(cudaMalloc(&buf, nn * (7 + 1 + 1 + 1 + 1) * 4));
+  float* d_rays = reinterpret_cast<float*>(buf);
+  uint32_t* d_seeds = reinterpret_cast<uint32_t*>(d_rays + 7 * nn);
+  float* d_t = reinterpret_cast<float*>(d_seeds + nn);
+  int32_t* d_index = reinterpret_cast<int32_t*>(d_t + nn);
+  uint32_t* d_rng = reinterpret_cast<uint32_t*>(d_index + nn);
+  SceneDesc desc = scene->desc;
+  desc.flat_cull = g_cull_enabled ? 1u : 0u;
+  cudaError_t e = cudaMemcpy(d_rays, rays7, nn * 28, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_seeds, seeds, nn * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_probe_rays(desc, n, d_rays, d_seeds, mode, d_t, d_index, d_rng, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(out_t, d_t, nn * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_index, d_index, nn * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_rng, d_rng, nn * 4, cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  if (e != cudaSuccess) return cuda_fail(e, "pt_debug_closest_hit");
+  return PT_OK;
+}
+
+// Debug aid (not part of pt_abi.h): what the last cost probe on this scene said: {heavy rate, express CTAs, mean scans per
+// sample x 1000, share of the work in heavy pixels x 1000, deepest probed sample}; zeros when no probe has run.
+int pt_debug_frame_tuning(pt_device_scene* scene, int out[5]) {
+  for (int k = 0; k < 5; ++k) out[k] = 0;
+  if (!scene || !scene->last_tuning) return PT_OK;
+  PT_CUDA(cudaSetDevice(scene->device));
+  PT_CUDA(cudaDeviceSynchronize());
+  FrameTuning t;
+  PT_CUDA(cudaMemcpy(&t, scene->last_tuning, sizeof t, cudaMemcpyDeviceToHost));
+  out[0] = t.heavy_rate, out[1] = t.n_express, out[2] = t.mean_scans_x1000, out[3] = t.heavy_share_x1000, out[4] = t.max_scans;
+  return PT_OK;
+}
+
+// Debug aid (not part of pt_abi.h): staged + resolved framebuffer stores on / off.
+int pt_debug_set_fb_stage(int on) {
+  g_fb_stage_enabled = on;
   return PT_OK;
 }
 

@@ -33,13 +33,26 @@ struct HeavyQueue {
   unsigned int stamp;    // (launch number; informational)
 };
 
+// What the cost probe says about the frame, computed on the device by the tile-order kernel and read by the render
+// kernel at its start (no host round trip): how many scans a sample takes on average, how much of the work sits in
+// pixels far above that, and the scheduling knobs derived from the two.
+struct FrameTuning {
+  int heavy_rate;        // a pixel is HEAVY (handed to the express CTAs) above kHeavyBase + heavy_rate * samples scans
+  int n_express;         // CTAs that only serve the hand-off queue
+  int mean_scans_x1000;  // probed scans per sample, x 1000
+  int heavy_share_x1000; // share of the probed work in pixels above 4 x the mean, x 1000
+  int max_scans;         // deepest probed sample
+  int pad[3];
+};
+
 struct RenderParams {
   SceneDesc scene;
   pt_camera cam;
   int width, height, spp, depth;
   pt_region region;
-  float* out;               // device (or peer-mapped) pointer
+  float* out;               // device (or peer-mapped) pointer: the caller's packed float3 rows, or the float4 staging rows
   long long out_row_pitch;  // floats
+  int out_pixel_floats;     // 3: `out` is the caller's framebuffer (scalar stores); 4: the staging buffer (one 16-byte store per pixel)
   // progressive rendering (pt_render_resume*): this launch traces samples [spp_from, spp) of every pixel; the per-pixel
   // state {sum r, g, b, RNG bits} is read when spp_from > 0 and written back when `state` is set
   float* state;             // 4 floats per pixel of the region, or null
@@ -54,6 +67,7 @@ struct RenderParams {
   unsigned int staged_bytes;          // wavefront kernel: bytes of the arena kept in shared memory (set by the launcher)
   unsigned int tree_list_bytes;       // wavefront kernel: dynamic shared memory behind them for the tree lists (set by the launcher)
   int n_express;                      // wavefront kernel: CTAs that only serve the hand-off queue (< 0 = automatic)
+  const FrameTuning* tuning;          // wavefront kernel: the cost probe's verdict (null: no probe ran; the defaults apply)
   // pixel order of the wavefront kernel (queue position -> pixel)
   int order_mode;                     // 0 = scrambled, 1 = tiles in `tile_order` (heaviest first), 2 = cost probe grid
   const int* tile_order;              // order_mode 1: tile ids (kTile x kTile pixels) in processing order
@@ -74,7 +88,18 @@ constexpr int kProbeStep = 2;  // the cost probe traces every kProbeStep-th pixe
 
 // Sort the region's tiles by probed cost, heaviest first (one small kernel).  `scratch` holds n_tiles ints.
 cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
-                              int* tile_order, int* scratch, cudaStream_t stream);
+                              int* tile_order, int* scratch, FrameTuning* tuning, int grid, int n_express_forced, cudaStream_t stream);
+int wave_grid(int device);  // CTAs of a wavefront launch on this device
+
+// The staged framebuffer {r, g, b, -} x (w x h) -> the caller's packed float3 rows, whole 16-byte stores, coalesced
+// (w must be a multiple of 4 and `out` rows 16-byte aligned).
+cudaError_t launch_resolve_fb(const float* stage, int w, int h, float* out, long long out_row_pitch, cudaStream_t stream);
+
+// Test hook: the closest-hit scan (render.hpp:30-51) of n given rays, one thread per ray, each with its own generator
+// state: t, the hit object's index in the scene's vector (-1: none), the generator afterwards.  mode 0 = the product's
+// scan (chunk boxes, flat trees, grazing index; vector order for rays that can meet a NaN), 1 = vector order for all.
+cudaError_t launch_probe_rays(const SceneDesc& scene, int n, const float* d_rays7, const uint32_t* d_seeds, int mode, float* d_t,
+                              int32_t* d_index, uint32_t* d_rng, cudaStream_t stream);
 
 int max_smem_blob_bytes(int device);
 cudaError_t launch_render(const RenderParams& p, int device, int grid_override, cudaStream_t stream,

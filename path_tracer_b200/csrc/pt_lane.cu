@@ -178,6 +178,29 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
   if ((threadIdx.x & 31) == 0 && p.counters) atomicAdd(p.counters, (unsigned long long)warp_scans);
 }
 
+// ---------------------------------------------------------------- ray-level test hook
+__global__ void __launch_bounds__(128) probe_rays_kernel(const SceneDesc sc, int n, const float* __restrict__ rays, const uint32_t* __restrict__ seeds,
+                                                         int mode, float* __restrict__ out_t, int32_t* __restrict__ out_index,
+                                                         uint32_t* __restrict__ out_rng) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const SceneView sv = scene_view(sc, sc.blob);
+  Ray ray;
+  ray.o = v3(rays[7 * i], rays[7 * i + 1], rays[7 * i + 2]);
+  ray.d = v3(rays[7 * i + 3], rays[7 * i + 4], rays[7 * i + 5]);
+  ray.tm = rays[7 * i + 6];
+  Rng rng { seeds[i] };
+  const Best b = mode == 0 ? closest_hit<false, true>(sc, sv, ray, rng, true, 0, 1) : closest_hit_in_order<false>(sc, sv, ray, rng);
+  const int key = b.id < 0 ? 0 : key_of(sc, b.id);
+  out_t[i] = b.t, out_index[i] = b.id < 0 ? -1 : (key < 0 ? -1 - key : key), out_rng[i] = rng.s;
+}
+cudaError_t launch_probe_rays(const SceneDesc& scene, int n, const float* d_rays7, const uint32_t* d_seeds, int mode, float* d_t,
+                              int32_t* d_index, uint32_t* d_rng, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  probe_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(scene, n, d_rays7, d_seeds, mode, d_t, d_index, d_rng);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_lane(const RenderParams& p, int device, int grid_override, cudaStream_t stream, LaunchInfo* info) {
   int sms = 0;
   cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

@@ -470,6 +470,32 @@ void compute_cull_boxes(const PackedScene& ps, float cam_time0, float cam_time1,
   }
 }
 
+void build_key_tables(const PackedScene& ps, std::vector<int32_t>& keys, uint32_t key_base[6], std::vector<int32_t>& object_id) {
+  keys.clear();
+  key_base[G_SPHERE] = (uint32_t)keys.size();
+  for (const auto& a : ps.sphere_aux) keys.push_back(a.key);
+  key_base[G_MOVING_SPHERE] = (uint32_t)keys.size();
+  for (const auto& a : ps.moving_aux) keys.push_back(a.key);
+  key_base[G_RECT] = (uint32_t)keys.size();
+  for (const auto& a : ps.rect_aux) keys.push_back(a.key);
+  key_base[G_TRIANGLE] = (uint32_t)keys.size();
+  for (const auto& a : ps.tri_aux) keys.push_back(a.key);
+  key_base[G_BOX] = (uint32_t)keys.size();
+  for (const auto& a : ps.box_aux) keys.push_back(a.key);
+  key_base[G_MEDIUM] = (uint32_t)keys.size();
+  for (const auto& a : ps.media) keys.push_back(a.key);
+  // a sphere's key is -1 - index, any other object's is the index (pt_packed.h); padding spheres have no material
+  object_id.assign(std::max<uint32_t>(ps.n_objects, 1u), -1);
+  for (size_t i = 0; i < ps.rect_aux.size(); ++i) object_id[(size_t)ps.rect_aux[i].key] = make_id(G_RECT, (int)i);
+  for (size_t i = 0; i < ps.tri_aux.size(); ++i) object_id[(size_t)ps.tri_aux[i].key] = make_id(G_TRIANGLE, (int)i);
+  for (size_t i = 0; i < ps.box_aux.size(); ++i) object_id[(size_t)ps.box_aux[i].key] = make_id(G_BOX, (int)i);
+  for (size_t i = 0; i < ps.media.size(); ++i) object_id[(size_t)ps.media[i].key] = make_id(G_MEDIUM, (int)i);
+  for (size_t i = 0; i < ps.sphere_aux.size(); ++i)
+    if (ps.sphere_aux[i].material >= 0) object_id[(size_t)(-1 - ps.sphere_aux[i].key)] = make_id(G_SPHERE, (int)i);
+  for (size_t i = 0; i < ps.moving_aux.size(); ++i)
+    if (ps.moving_aux[i].material >= 0) object_id[(size_t)(-1 - ps.moving_aux[i].key)] = make_id(G_MOVING_SPHERE, (int)i);
+}
+
 int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   out = PackedScene {};
   if ((sc.n_hittables && !sc.order) || (sc.n_spheres && !sc.spheres) || (sc.n_rects && !sc.rects) ||

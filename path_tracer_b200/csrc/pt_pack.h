@@ -45,6 +45,10 @@ struct CullBoxes {
 };
 void compute_cull_boxes(const PackedScene& ps, float cam_time0, float cam_time1, CullBoxes& out);
 
+// The side tables both kernels index by scan id: the tie-break keys of every object (keys[key_base[type] + index]) and
+// the way back, original object index -> scan id (-1: no such object).
+void build_key_tables(const PackedScene& ps, std::vector<int32_t>& keys, uint32_t key_base[6], std::vector<int32_t>& object_id);
+
 // Returns PT_OK or a PT_ERR_* code with a message in `error`.
 int pack_scene(const pt_scene& scene, PackedScene& out, std::string& error);
 

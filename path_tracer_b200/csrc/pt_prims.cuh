@@ -668,12 +668,85 @@ __device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, 
   return best;
 }
 
+// THE SCAN IN VECTOR ORDER.  The (minimum t, maximum key) rule is the sequential scan's result only while every t
+// is a number.  A rectangle or box side whose plane contains the ray (d_k == 0 exactly and o_k == k) has t = 0 / 0 =
+// NaN, which the reference ACCEPTS (rectangle.hpp:35-41 reject with `t < min || t > max`) and which then poisons its
+// running closest hit: every later sphere is rejected (`temp < NaN`), every later flat object accepted.  No order-
+// independent rule reproduces that, so rays that can meet a NaN -- an exactly zero direction component, or anything
+// not finite -- are scanned the reference's way: object by object in vector order against the running closest hit.
+// So are rays whose direction is outside [2^-20, 2^20]: the error bounds behind the miss filter and the box tests
+// assume no underflow or overflow in d . d (found by tests/host/scan_check.cpp: a direction of length 1e-23).
+// Out of line (it is rare: pixel (0, 0), whose generator returns zeros forever, and hand-made cameras).
+PT_DEV bool needs_in_order(const Ray& r) {
+  const float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+  const float dmax = fmaxf(fmaxf(ax, ay), az), dmin = fminf(fminf(ax, ay), az);
+  const float all = ((r.o.x + r.o.y) + r.o.z) + ((r.d.x + r.d.y) + r.d.z);  // (fminf / fmaxf drop a NaN: catch it here; inf - inf is NaN)
+  return !(dmin > 0.f && dmax >= kCullDirMin && dmax <= kCullDirMax && all - all == 0.f);
+}
+template <bool kSmem>
+__device__ __noinline__ Best closest_hit_in_order(const SceneDesc* scp, const float4* sphere, const float4* moving, const float4* rect,
+                                                  const float4* triangle, const float4* box, Ray r, Rng* rng) {
+  const SceneDesc& sc = *scp;
+  Best best { kInf, -1 };
+  float closest = kInf;  // render.hpp:35
+  const int n = (int)sc.n_objects;
+#pragma unroll 1
+  for (int i = 0; i < n; ++i) {
+    const int id = sc.object_id[i];
+    if (id < 0) continue;
+    const int idx = id & (int)kIdMask;
+    float t, ra, rb;
+    bool hit = false;
+    switch (id >> kIdShift) {
+      case G_SPHERE: {
+        const float4 s = ld4<kSmem>(sphere + sphere_slot(idx));
+        hit = sphere_hit_t(r, v3(s.x, s.y, s.z), exact_r2(sc.sphere_aux, idx), kTMin, closest, t);
+        break;
+      }
+      case G_MOVING_SPHERE: {
+        const float4 s = ld4<kSmem>(moving + moving_slot(idx)), v = ld4<kSmem>(moving + moving_slot(idx) + 2 * kSphereChunk);
+        const SphereAux* aux = sc.moving_aux + idx;
+        const V3 center = moving_center(v3(s.x, s.y, s.z), v3(v.x, v.y, v.z), fdiv(fsub(r.tm, aux->time0), aux->den));
+        hit = sphere_hit_t(r, center, exact_r2(sc.moving_aux, idx), kTMin, closest, t);
+        break;
+      }
+      case G_RECT: {
+        const float4 q0 = ld4<kSmem>(rect + 2 * idx), q1 = ld4<kSmem>(rect + 2 * idx + 1);
+        hit = rect_hit_t(r, __float_as_int(q1.y), q0.x, q0.y, q0.z, q0.w, q1.x, kTMin, closest, t, ra, rb);
+        break;
+      }
+      case G_TRIANGLE: {
+        const float4 v0 = ld4<kSmem>(triangle + 3 * idx), e1 = ld4<kSmem>(triangle + 3 * idx + 1), e2 = ld4<kSmem>(triangle + 3 * idx + 2);
+        hit = triangle_hit_t(r, v3(v0.x, v0.y, v0.z), v3(e1.x, e1.y, e1.z), v3(e2.x, e2.y, e2.z), kTMin, closest, t);
+        break;
+      }
+      case G_BOX: {
+        const float4 p0 = ld4<kSmem>(box + 2 * idx), p1 = ld4<kSmem>(box + 2 * idx + 1);
+        hit = box_hit_t(r, v3(p0.x, p0.y, p0.z), v3(p1.x, p1.y, p1.z), kTMin, closest, t, ra, rb) >= 0;
+        break;
+      }
+      default:
+        hit = medium_hit_t(sc.media[idx], r, kTMin, closest, *rng, t);
+        break;
+    }
+    if (hit) closest = t, best.t = t, best.id = id;  // render.hpp:44-47
+  }
+  return best;
+}
+template <bool kSmem> PT_DEV Best closest_hit_in_order(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng) {
+  return closest_hit_in_order<kSmem>(&sc, sv.sphere(), sv.moving(), sv.rect(), sv.triangle(), sv.box(), r, &rng);
+}
+
 // render.hpp:30-51 for one ray per TEAM: `member` in [0, team_size) takes every team_size-th object
 // of each group.  `act`: this lane's team carries a real ray (the others ride along so that the
 // warp stays converged on the shared loads and the shuffles).
 template <bool kSmem, bool kTrees = true>
 PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, bool act, int member,
                         int team_size) {
+  // a ray that can meet a NaN is scanned in vector order (above) by every member of its team, AFTER the team has
+  // ridden along here without a ray: the other teams of the warp need it for their full-warp shuffles
+  const bool in_order = act && needs_in_order(r);
+  act = act && !in_order;
   Best best { kInf, -1 };
   const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant
   CullRay cr;
@@ -714,6 +787,88 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
     }
   }
   if (team_size > 1) team_merge(sc, best, team_size);
+  if (in_order) best = closest_hit_in_order<kSmem>(sc, sv, r, rng);
+  return best;
+}
+
+// ---------------------------------------------------------------- one ray per WARP (the deep-pixel lane of pt_wave.cu)
+// All 32 lanes hold the same ray.  Sphere groups: lane l tests the box of chunk cb + l, the crossed chunks come back
+// as a ballot and are scanned two at a time -- lanes 0-15 one sphere each of the first, lanes 16-31 of the second --
+// with the usual two-phase test.  Every lane keeps a partial winner (its own running closest hit is a valid upper
+// bound for the boxes it tests); team_merge() joins them under the (t, key) rule.
+template <bool kSmem, bool kMoving>
+PT_DEV void scan_sphere_chunks_warp(const SceneDesc& sc, const float4* __restrict__ data, const float4* __restrict__ boxes,
+                                    const SphereAux* aux, int first_el, int end_el, int lane, const Ray& r, float a, float f,
+                                    const CullRay& cr, int type, Best& best) {
+  constexpr int kSlots = kMoving ? 4 * kSphereChunk : 2 * kSphereChunk;  // float4 per chunk
+  const float af = filter_a(a);
+  const int c_end = end_el / kSphereChunk;
+  const int half = lane >> 4, j = lane & (kSphereChunk - 1);
+#pragma unroll 1
+  for (int cb = first_el / kSphereChunk; cb < c_end; cb += 32) {
+    const int c = cb + lane;
+    unsigned hits = __ballot_sync(0xffffffffu, c < c_end && (int)chunk_bits<kSmem>(boxes + 2 * c, cr, best.t) < 0);
+#pragma unroll 1
+    while (hits) {
+      const int c0 = __ffs((int)hits) - 1;
+      hits &= hits - 1u;
+      int mine = cb + c0;
+      if (hits) {
+        const int c1 = __ffs((int)hits) - 1;
+        hits &= hits - 1u;
+        if (half) mine = cb + c1;
+      } else if (half) {
+        mine = -1;
+      }
+      if (mine >= 0) {
+        const float4* p = data + mine * kSlots + j;
+        if ((int)sphere_filter_bits<kSmem, kMoving>(p, f, r, af) < 0) {
+          float cx, cy, cz, r2f;
+          sphere_center<kSmem, kMoving>(p, f, cx, cy, cz, r2f);
+          const int i = mine * kSphereChunk + j;
+          sphere_roots_scan(sc, best, r, a, cx, cy, cz, exact_r2(aux, i), make_id(type, i));
+        }
+      }
+    }
+  }
+}
+
+// render.hpp:30-51 for one ray held by all 32 lanes of a warp: closest_hit() with a team of 32, the sphere groups
+// scanned warp-wide (above), flat objects one per lane, media replayed by every lane on its replica of the generator.
+template <bool kSmem, bool kTrees>
+PT_DEV Best closest_hit_warp(const SceneDesc& sc, const SceneView& sv, const Ray& r, Rng& rng, int lane) {
+  Best best { kInf, -1 };
+  const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant
+  CullRay cr;
+  const int cull_set = make_cull_ray(sc, r, cr);
+  const int n_groups = (int)sc.n_groups;
+  bool dirty = false;  // partial winners not merged yet
+#pragma unroll 1
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const Group g = sv.groups()[gi];
+    const int end = g.begin + g.count;
+    if (g.type == G_SPHERE) {
+      scan_sphere_chunks_warp<kSmem, false>(sc, sv.sphere(), sv.sphere_box() + cull_set * 2 * (int)sc.n_sphere_chunks, sc.sphere_aux,
+                                            g.begin, end, lane, r, a, 0.f, cr, G_SPHERE, best);
+      dirty = true;
+    } else if (g.type == G_MOVING_SPHERE) {
+      scan_sphere_chunks_warp<kSmem, true>(sc, sv.moving(), sv.moving_box() + cull_set * 2 * (int)sc.n_moving_chunks, sc.moving_aux,
+                                           g.begin, end, lane, r, a, fdiv(fsub(r.tm, g.time0), g.den), cr, G_MOVING_SPHERE, best);
+      dirty = true;
+    } else if (g.type == G_MEDIUM) {
+      // the medium sees the running closest hit of EVERY lower-index object (merge first) and commits unconditionally
+      if (dirty) team_merge(sc, best, 32), dirty = false;
+      float t;
+      if (medium_hit_t(sc.media[g.begin], r, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
+    } else {
+      if (kTrees && has_tree(sc, g))
+        best = scan_flat_tree<kSmem>(key_table(sc), flat_trees(sc, sv, g.type), g, r, lane, 32, best);
+      else
+        scan_flat_group<kSmem>(sc, sv, g, r, g.begin + lane, 32, best);
+      dirty = true;
+    }
+  }
+  if (dirty) team_merge(sc, best, 32);
   return best;
 }
 

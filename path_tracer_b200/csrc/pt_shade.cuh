@@ -244,7 +244,10 @@ PT_DEV void pixel_start(const RenderParams& p, int px, int py, const float* stat
 // The pixel is finished for this launch: render.hpp:102-105, and the state for a later pt_render_resume.
 PT_DEV void pixel_finish(const RenderParams& p, float* out_px, float* state_px, V3 acc, Rng rng, float fspp) {
   const V3 fin = vdivs(acc, fspp);
-  out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
+  if (p.out_pixel_floats == 4)  // staged: one aligned 16-byte store; launch_resolve_fb packs the rows afterwards
+    *reinterpret_cast<float4*>(out_px) = make_float4(fin.x, fin.y, fin.z, 0.f);
+  else
+    out_px[0] = fin.x, out_px[1] = fin.y, out_px[2] = fin.z;
   if (state_px) *reinterpret_cast<float4*>(state_px) = make_float4(acc.x, acc.y, acc.z, __uint_as_float(rng.s));
 }
 PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, int& py, float*& out_px, float*& state_px) {
@@ -265,7 +268,7 @@ PT_DEV bool queue_pixel(const RenderParams& p, unsigned long long pos, int& px, 
   }
   px = p.region.x0 + (int)xx;
   py = p.region.y0 + (int)k * p.region.y_stride;
-  out_px = p.out + (long long)k * p.out_row_pitch + 3ll * (long long)xx;
+  out_px = p.out + (long long)k * p.out_row_pitch + (long long)p.out_pixel_floats * (long long)xx;
   state_px = p.state ? p.state + 4ll * ((long long)k * p.state_row_pitch + (long long)xx) : nullptr;
   return true;
 }

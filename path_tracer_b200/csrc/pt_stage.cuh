@@ -53,26 +53,39 @@ PT_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- scene view
-// The kernels' view of the scan blob (in shared or global memory): nothing but the blob's base and the descriptor
-// that holds the offsets -- the arrays' addresses are formed where they are used (one load of the offset, which the
-// compiler hoists out of the loops) instead of living in a dozen 64-bit registers across the whole kernel.
+// The kernels' view of the scan blob (in shared or global memory).  The arrays of the hot loops are plain pointers (the
+// compiler keeps them in registers across the phases; forming them from the descriptor's offsets at every use cost the
+// default scene 4 % -- measured); the flat groups' trees, used by few scenes, are formed where they are used.
 struct SceneView {
+  const Group* groups_;
+  const float4 *sphere_, *moving_, *rect_, *triangle_, *box_, *sphere_box_, *moving_box_;
   const unsigned char* base;
   const SceneDesc* sc;
-  template <typename T> PT_DEV const T* at(uint32_t off) const { return reinterpret_cast<const T*>(base + off); }
-  PT_DEV const Group* groups() const { return at<Group>(sc->off_groups); }
-  PT_DEV const float4* sphere() const { return at<float4>(sc->off_sphere); }
-  PT_DEV const float4* moving() const { return at<float4>(sc->off_moving); }
-  PT_DEV const float4* rect() const { return at<float4>(sc->off_rect); }
-  PT_DEV const float4* triangle() const { return at<float4>(sc->off_triangle); }
-  PT_DEV const float4* box() const { return at<float4>(sc->off_box); }
-  PT_DEV const float4* sphere_box() const { return at<float4>(sc->off_sphere_box); }  // chunk boxes, set 0 first
-  PT_DEV const float4* moving_box() const { return at<float4>(sc->off_moving_box); }
-  PT_DEV const Tree* trees() const { return at<Tree>(sc->off_trees); }          // flat groups' box trees and grazing indices
-  PT_DEV const float4* nodes() const { return at<float4>(sc->off_nodes); }      // their boxes
-  PT_DEV const float4* tree_ids() const { return at<float4>(sc->off_tree_ids); }  // grazing index: the leaves' {g, triangle} lists
+  PT_DEV const Group* groups() const { return groups_; }
+  PT_DEV const float4* sphere() const { return sphere_; }
+  PT_DEV const float4* moving() const { return moving_; }
+  PT_DEV const float4* rect() const { return rect_; }
+  PT_DEV const float4* triangle() const { return triangle_; }
+  PT_DEV const float4* box() const { return box_; }
+  PT_DEV const float4* sphere_box() const { return sphere_box_; }  // chunk boxes, set 0 first
+  PT_DEV const float4* moving_box() const { return moving_box_; }
+  PT_DEV const Tree* trees() const { return reinterpret_cast<const Tree*>(base + sc->off_trees); }  // flat groups' box trees and grazing indices
+  PT_DEV const float4* nodes() const { return reinterpret_cast<const float4*>(base + sc->off_nodes); }  // their boxes
+  PT_DEV const float4* tree_ids() const { return reinterpret_cast<const float4*>(base + sc->off_tree_ids); }  // grazing index: {g, triangle} lists
 };
-PT_DEV SceneView scene_view(const SceneDesc& sc, const unsigned char* blob_base) { return SceneView { blob_base, &sc }; }
+PT_DEV SceneView scene_view(const SceneDesc& sc, const unsigned char* blob_base) {
+  SceneView sv;
+  sv.groups_ = reinterpret_cast<const Group*>(blob_base + sc.off_groups);
+  sv.sphere_ = reinterpret_cast<const float4*>(blob_base + sc.off_sphere);
+  sv.moving_ = reinterpret_cast<const float4*>(blob_base + sc.off_moving);
+  sv.rect_ = reinterpret_cast<const float4*>(blob_base + sc.off_rect);
+  sv.triangle_ = reinterpret_cast<const float4*>(blob_base + sc.off_triangle);
+  sv.box_ = reinterpret_cast<const float4*>(blob_base + sc.off_box);
+  sv.sphere_box_ = reinterpret_cast<const float4*>(blob_base + sc.off_sphere_box);
+  sv.moving_box_ = reinterpret_cast<const float4*>(blob_base + sc.off_moving_box);
+  sv.base = blob_base, sv.sc = &sc;
+  return sv;
+}
 
 template <bool kSmem> PT_DEV float4 ld4(const float4* p) {
   if constexpr (kSmem)

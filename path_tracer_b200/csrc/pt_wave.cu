@@ -88,6 +88,9 @@ namespace {
 #ifndef PT_EXPRESS_POOL
 #define PT_EXPRESS_POOL 64
 #endif
+#ifndef PT_EXPRESS_RULE  // (calibrated on the BASELINE configs: tools/express_sweep.py)
+#define PT_EXPRESS_RULE(grid, share) (((grid) * 23 + 100) / 200)
+#endif
 #ifndef PT_WAVE_ITEMS
 #define PT_WAVE_ITEMS 4096
 #endif
@@ -102,6 +105,7 @@ constexpr int kWaveItems = PT_WAVE_ITEMS;                  // (ray, chunk) items
 constexpr int kWaveItemsStatic = kWaveItems * 3 / 8;       // ... of static spheres (from the front of the list)
 constexpr int kWaveItemsMoving = kWaveItems - kWaveItemsStatic;  // ... of moving spheres (from the back)
 constexpr unsigned long long kNoHit64 = 0x7f800000ffffffffull;  // {t = +inf, no object}
+constexpr unsigned long long kResolved64 = 0xffffffffffffffffull;  // the ray's scan was done in vector order (hit_t / hit_id hold it)
 #ifndef PT_FINE_RAYS
 #define PT_FINE_RAYS 160
 #endif
@@ -138,6 +142,8 @@ struct WavePool {
   int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
   int n_tgroups;   // flat groups with a tree in front of the first constant_medium (expanded breadth first: wave_tree_expand)
   int tgroups[kMaxTreeGroups];
+  int heavy_rate;  // hand-off threshold of this frame (FrameTuning)
+  int n_express;   // express CTAs of this frame
   int tree_passes; // tree passes per round: the deepest of those trees has this many levels above its leaves
   int tl_n[3], tl_off[3], tl_cap[3];  // the tree lists (in dynamic shared memory behind the staged scene): node items of pass 0 and 1, leaf items
   int free_count;
@@ -322,7 +328,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
   const unsigned lane_lt = (1u << lane) - 1u;
   const HeavyQueue& hq = p.heavy;
-  const bool express = (int)blockIdx.x < p.n_express;  // this CTA only serves the hand-off queue
+  // the frame's scheduling knobs: the cost probe's verdict when one ran (read from device memory: no host round trip),
+  // else the launcher's defaults.  (The probe itself runs with n_express = 0 and no tuning.)
+  const int n_express = p.tuning ? min(__ldg(&p.tuning->n_express), (int)gridDim.x - 1) : p.n_express;
+  const int heavy_rate_frame = p.tuning ? __ldg(&p.tuning->heavy_rate) : kHeavyRate;
+  const unsigned long long express_positions = p.order_mode == 1 ? min((unsigned long long)n_express * (unsigned long long)kExpressPool, p.n_positions) : 0ull;
+  const bool express = (int)blockIdx.x < n_express;  // this CTA only serves the hand-off queue
   const bool sequential_scan = sc.n_late_sphere_groups != 0u;
   const int n_groups = (int)sc.n_groups;
   unsigned int n_scans = 0;
@@ -336,12 +347,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       unsigned long long pos;
       if (express) {
         pos = atomicAdd(p.pixel_counter + 1, 1ull);
-        if (pos >= p.express_positions) {
+        if (pos >= express_positions) {
           atomicExch(&W.pixel_dry, 1);
           return false;
         }
       } else {
-        pos = p.express_positions + atomicAdd(p.pixel_counter, 1ull);
+        pos = express_positions + atomicAdd(p.pixel_counter, 1ull);
         if (pos >= p.n_positions) {
           atomicExch(&W.pixel_dry, 1);
           if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
@@ -570,7 +581,25 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     __syncthreads();
   }
 
-  for (unsigned int round = 0;; ++round) {
+  // ---- DEEP WARPS (-DPT_DEEP_WARPS; an experiment, compiled out by default).  The deepest pixels of an image are
+  // serial chains of thousands of bounces (a pixel's samples are strictly serial, render.hpp:94-101), so what bounds
+  // the frame is the LATENCY of one bounce: 17 000 cycles in a short round of the phase machine (four CTA barriers,
+  // every phase waiting for its slowest thread).  With the macro the warps of an express CTA leave the phase machine:
+  // each traces ONE pixel at a time, all 32 lanes holding the pixel's state and splitting every scan
+  // (closest_hit_warp), with shuffles and ballots instead of barriers and shared-memory lists.  Same device functions,
+  // same bits (the GPU suite passes with it) -- but MEASURED SLOWER: 28 such warps per SM share the issue slots, a
+  // bounce costs each of them ~2 000 warp instructions for ONE ray, and the express CTAs' throughput falls below what
+  // the hand-off queue brings (default scene: 38.8 ms per frame against 29.1 ms, pixels waiting 13 ms in the queue; with
+  // 24 / 32 express CTAs 35.4 / 34.5 ms).  A short round moves ~35 rays in 17 000 cycles: the same throughput per SM, and
+  // it is throughput the express CTAs lack, not only latency.
+#ifdef PT_DEEP_WARPS
+  const bool deep = express && p.order_mode != 2;
+#else
+  const bool deep = false;
+#endif
+  bool go_deep = deep;  // (a regular CTA joins them when its own pixels have run out: -DPT_SERVICE_DEEP)
+
+  for (unsigned int round = 0; !deep; ++round) {
     if (mode == 1) {
       // ---- hand-off service: fill the free pool slots from the global queue (polled every 8th round: a poll is
       // two round trips to L2, and these rounds are the frame's critical path)
@@ -631,7 +660,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           if (p.counters && !express) atomicMin(p.counters + 5, globaltimer_ns()), atomicMax(p.counters + 6, globaltimer_ns());
         }
         __syncthreads();
+#ifdef PT_SERVICE_DEEP
+        go_deep = true;
+        break;
+#else
         continue;
+#endif
       }
       // idle: every producer is done (the launch is cooperative: every CTA is resident and will report) and every entry
       // has been claimed => nothing will ever arrive again
@@ -680,12 +714,23 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int e = fine ? w / units_per_ray : w;
         const int slot = (int)W.list_a[e];
         const Ray ray = load_ray(slot);
+        const int unit = fine ? w - e * units_per_ray : 0;
+        if (needs_in_order(ray)) {
+          // a ray that can meet a NaN (pt_prims.cuh): the reference's own scan, in vector order, here and now; ITEMS
+          // and LATE leave the ray alone
+          if (unit == 0) {
+            Rng rng { W.rng[slot] };
+            const Best best = closest_hit_in_order<kSmem>(sc, sv, ray, rng);
+            W.hit_t[slot] = best.t, W.hit_id[slot] = best.id, W.rng[slot] = rng.s;
+            W.best64[slot] = kResolved64;
+          }
+          continue;
+        }
         CullRay cr;
         const int cull_set = make_cull_ray(sc, ray, cr);
         const float a = vdot(ray.d, ray.d);  // sphere.hpp:69
         Best inl { kInf, -1 };
         unsigned long long v = kNoHit64;
-        const int unit = fine ? w - e * units_per_ray : 0;
         if (kTrees && fine && unit >= W.n_blocks) {  // short rounds: one flat tree of the ray
           emit_flat_items(slot, ray, unit - W.n_blocks, v);
           if (v != kNoHit64) atomicMin(&W.best64[slot], v);
@@ -834,6 +879,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             const int2 fo = W.flats[j];
             const int slot = (int)W.list_a[(w - f_base) - j * n];
             const Ray ray = load_ray(slot);
+            if (needs_in_order(ray)) continue;  // (scanned in vector order in BOXES)
             Best b { kInf, -1 };
             if ((fo.x & 255) == G_BOX) {
               const float4 p0 = ld4<kSmem>(sv.box() + 2 * fo.y);
@@ -862,9 +908,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       if (sequential_scan) {
         best.t = W.hit_t[slot], best.id = W.hit_id[slot];
       } else {
-        best = unpack_winner(sc, W.best64[slot]);
+        const unsigned long long w64 = W.best64[slot];
+        best = unpack_winner(sc, w64);
         const int late = W.first_late_group;
-        if (late < n_groups) {
+        if (w64 == kResolved64) {  // scanned in vector order in BOXES, media included
+          best.t = W.hit_t[slot], best.id = W.hit_id[slot];
+        } else if (late < n_groups) {
           // from the first constant_medium on, in group order against the running closest hit; a medium commits
           // unconditionally and may draw from the pixel's stream (constant_medium.hpp:52-65)
           const Ray ray = load_ray(slot);
@@ -906,7 +955,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
       unit_base[kWaveKinds] = units;
     }
-    const int heavy_rate = *reinterpret_cast<volatile int*>(&W.pixel_dry) ? kHeavyRateDry : kHeavyRate;
+    const int heavy_rate = heavy_rate_frame;
     for (int u = warp; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
       int kind = 0, e = 0, e_end = 0;
 #pragma unroll
@@ -990,6 +1039,95 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 #endif
   }
 
+#ifdef PT_DEEP_WARPS
+  if (go_deep) {
+    if (deep && tid == 0) {  // an express CTA hands nothing off: it counts as "finished with its regular work" from the start
+      __threadfence();
+      atomicAdd(hq.ctrl + 2, 1u);
+    }
+    bool have = false;
+    uint32_t pixq = 0u;
+    int px = 0, py = 0, sample = 0, bounce = 0;
+    Rng rng { 0u };
+    Ray ray { v3(0.f, 0.f, 0.f), v3(0.f, 0.f, 0.f), 0.f };
+    V3 att = v3(1.f, 1.f, 1.f), acc = v3(0.f, 0.f, 0.f);
+    for (;;) {
+      if (!have) {
+        // (1) the reserved head of the LPT order
+        uint32_t got = 0xffffffffu;
+        if (lane == 0) {
+          uint32_t q;
+          Rng r0;
+          int x, y, s0;
+          V3 a0;
+          if (next_pixel(q, r0, x, y, a0, s0)) got = q;
+        }
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (got != 0xffffffffu) {
+          pixq = got;
+          float *unused, *state_px;
+          queue_pixel(p, pixq, px, py, unused, state_px);
+          pixel_start(p, px, py, state_px, rng, acc, sample);
+          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          att = v3(1.f, 1.f, 1.f), bounce = 0, have = true;
+        } else {
+          // (2) the hand-off queue: lane 0 claims an entry, the lanes read one word each
+          unsigned int hpos = 0u;
+          int ok = 0;
+          if (lane == 0) ok = take_heavy(hpos) ? 1 : 0;
+          ok = __shfl_sync(0xffffffffu, ok, 0), hpos = __shfl_sync(0xffffffffu, hpos, 0);
+          if (ok) {
+            const float* e = hq.entries + (size_t)(hpos & (hq.cap - 1u)) * kHeavyEntryWords;
+            const float wv = lane < kHeavyEntryWords ? __ldcg(e + lane) : 0.f;
+#define PT_WORD(k) __shfl_sync(0xffffffffu, wv, (k))
+            pixq = __float_as_uint(PT_WORD(0)), rng.s = __float_as_uint(PT_WORD(1));
+            sample = __float_as_int(PT_WORD(2)), bounce = __float_as_int(PT_WORD(3));
+            ray.o = v3(PT_WORD(4), PT_WORD(5), PT_WORD(6)), ray.d = v3(PT_WORD(7), PT_WORD(8), PT_WORD(9)), ray.tm = PT_WORD(10);
+            att = v3(PT_WORD(11), PT_WORD(12), PT_WORD(13)), acc = v3(PT_WORD(14), PT_WORD(15), PT_WORD(16));
+            const uint32_t queued_at = __float_as_uint(PT_WORD(17));  // (every lane takes part in every shuffle)
+            if (lane == 0) {
+              if (p.counters) {  // stats: how long did the pixel wait in the queue
+                const unsigned long long waited = (uint32_t)((uint32_t)globaltimer_ns() - queued_at);
+                atomicAdd(p.counters + 12, waited), atomicMax(p.counters + 13, waited);
+              }
+              release_heavy(hpos);
+            }
+#undef PT_WORD
+            float *unused, *state_px;
+            queue_pixel(p, pixq, px, py, unused, state_px);
+            have = true;
+          } else {
+            // nothing right now: finished when every CTA has reported and every entry has been claimed
+            int done = 0;
+            if (lane == 0) done = (ld_volatile_u32(hq.ctrl + 2) >= gridDim.x && ld_volatile_u32(hq.ctrl + 0) == ld_volatile_u32(hq.ctrl + 1)) ? 1 : 0;
+            if (__shfl_sync(0xffffffffu, done, 0)) break;
+            __nanosleep(400);
+            continue;
+          }
+        }
+      }
+      const Best best = closest_hit_warp<kSmem, kTrees>(sc, sv, ray, rng, lane);
+      if (lane == 0) ++n_scans;
+      V3 contribution;
+      if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
+        acc = vadd(acc, contribution);  // the path ended: render.hpp:100-105
+        if (++sample == p.spp) {
+          if (lane == 0) {
+            int x, y;
+            float *out_px, *state_px;
+            queue_pixel(p, pixq, x, y, out_px, state_px);
+            pixel_finish(p, out_px, state_px, acc, rng, fspp);
+          }
+          have = false;
+        } else {
+          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          att = v3(1.f, 1.f, 1.f), bounce = 0;
+        }
+      }
+    }
+  }
+
+#endif
   if (p.counters && lane == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   unsigned int warp_scans = n_scans;
 #pragma unroll
@@ -998,14 +1136,27 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 }
 
 // ---------------------------------------------------------------- LPT tile order
+// How many of `grid` CTAs only serve the hand-off queue.  Without a probe: 17 of 148 (measured best on the default
+// scene).  With one: by the share of the probed work that sits in pixels above four times the average.
+__host__ __device__ inline int express_ctas(int grid, int heavy_share_x1000) {
+  if (grid < 64) return 0;
+  int n = (grid * 23 + 100) / 200;
+  if (heavy_share_x1000 >= 0) n = PT_EXPRESS_RULE(grid, heavy_share_x1000);
+  return n < 1 ? 1 : (n > grid / 3 ? grid / 3 : n);
+}
+
 // One block: bin the tiles by probed cost (sum of the probes inside the tile), then list them from the
 // most expensive bin to the cheapest (counting sort; the order inside a bin does not matter).
 constexpr int kCostBins = 1024;
 __global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict__ probe_cost, int region_w, int region_h,
                                                            int tiles_x, int tiles_y, int* __restrict__ tile_order,
-                                                           int* __restrict__ tile_bin) {
+                                                           int* __restrict__ tile_bin, FrameTuning* __restrict__ tuning, int grid,
+                                                           int n_express_forced) {
   __shared__ int hist[kCostBins];
   __shared__ int start[kCostBins];
+  __shared__ unsigned long long total, heavy;
+  __shared__ int deepest;
+  if (threadIdx.x == 0) total = 0ull, heavy = 0ull, deepest = 0;
   const int n_tiles = tiles_x * tiles_y;
   const int pw = (region_w + kProbeStep - 1) / kProbeStep, ph = (region_h + kProbeStep - 1) / kProbeStep;
   for (int b = threadIdx.x; b < kCostBins; b += blockDim.x) hist[b] = 0;
@@ -1029,11 +1180,66 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict_
   }
   __syncthreads();
   for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) tile_order[atomicAdd(&start[tile_bin[t]], 1)] = t;
+  // ---- what the probe says about the frame (FrameTuning, pt_kernel.h)
+  const int n_probes = pw * ph;
+  unsigned long long mine = 0ull;
+  int my_max = 0;
+  for (int i = threadIdx.x; i < n_probes; i += blockDim.x) mine += (unsigned long long)probe_cost[i], my_max = max(my_max, probe_cost[i]);
+  atomicAdd(&total, mine), atomicMax(&deepest, my_max);
+  __syncthreads();
+  const unsigned long long sum = total;
+  mine = 0ull;
+  for (int i = threadIdx.x; i < n_probes; i += blockDim.x)
+    if (4ull * sum < (unsigned long long)probe_cost[i] * (unsigned long long)n_probes) mine += (unsigned long long)probe_cost[i];  // cost > 4 x mean
+  atomicAdd(&heavy, mine);
+  __syncthreads();
+  if (threadIdx.x == 0 && tuning) {
+    FrameTuning t;
+    t.mean_scans_x1000 = (int)(1000ull * sum / (unsigned long long)max(n_probes, 1));
+    t.heavy_share_x1000 = (int)(1000ull * heavy / (sum ? sum : 1ull));
+    t.max_scans = deepest;
+    // a pixel is heavy when it spends more than four times the frame's average per sample (the default scene: 2.6 scans
+    // per sample, rate 10); never below the default
+    t.heavy_rate = max(kHeavyRate, (int)((4ull * sum + (unsigned long long)n_probes / 2ull) / (unsigned long long)max(n_probes, 1)));
+    t.n_express = n_express_forced >= 0 ? n_express_forced : express_ctas(grid, t.heavy_share_x1000);
+    t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    *tuning = t;
+  }
 }
 
 cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
-                              int* tile_order, int* scratch, cudaStream_t stream) {
-  tile_order_kernel<<<1, 1024, 0, stream>>>(probe_cost, region_w, region_h, tiles_x, tiles_y, tile_order, scratch);
+                              int* tile_order, int* scratch, FrameTuning* tuning, int grid, int n_express_forced, cudaStream_t stream) {
+  tile_order_kernel<<<1, 1024, 0, stream>>>(probe_cost, region_w, region_h, tiles_x, tiles_y, tile_order, scratch, tuning, grid,
+                                            n_express_forced);
+  return cudaGetLastError();
+}
+int wave_grid(int device) {
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms * PT_WAVE_BLOCKS_PER_SM;
+}
+
+// ---------------------------------------------------------------- framebuffer resolve
+// Pixels finish one at a time, in the LPT tile order, and a packed float3 pixel is only 4-byte aligned: the render
+// kernels therefore write each finished pixel with ONE 16-byte store into a float4 staging image, and this pass
+// turns four staged pixels into three 16-byte stores of the caller's rows (render.hpp:102-105's fb[y][x] = ...),
+// a warp writing 1 536 contiguous bytes -- to local HBM or, at N > 1, straight into rank 0's peer-mapped framebuffer.
+__global__ void __launch_bounds__(256) resolve_fb_kernel(const float4* __restrict__ stage, int quads_per_row, int h, float* __restrict__ out,
+                                                         long long out_row_pitch) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)quads_per_row * h) return;
+  const int row = (int)(idx / quads_per_row), q = (int)(idx - (long long)row * quads_per_row);
+  const float4* s = stage + ((long long)row * quads_per_row + q) * 4;
+  const float4 a = s[0], b = s[1], c = s[2], d = s[3];
+  float4* o = reinterpret_cast<float4*>(out + (long long)row * out_row_pitch + 12ll * q);
+  o[0] = make_float4(a.x, a.y, a.z, b.x);
+  o[1] = make_float4(b.y, b.z, c.x, c.y);
+  o[2] = make_float4(c.z, d.x, d.y, d.z);
+}
+cudaError_t launch_resolve_fb(const float* stage, int w, int h, float* out, long long out_row_pitch, cudaStream_t stream) {
+  const long long n = (long long)(w / 4) * h;
+  if (n <= 0) return cudaSuccess;
+  resolve_fb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(stage), w / 4, h, out, out_row_pitch);
   return cudaGetLastError();
 }
 
@@ -1081,7 +1287,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
     // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
-    q.n_express = p.n_express >= 0 ? p.n_express : (grid >= 64 ? (grid * 23 + 100) / 200 : 0);  // 17 of 148: measured best on the default scene
+    q.n_express = p.n_express >= 0 ? p.n_express : express_ctas(grid, -1);  // (a frame with a cost probe brings its own: FrameTuning)
     if (q.n_express >= grid) q.n_express = grid - 1;
     if (p.order_mode == 2) {
       q.n_express = 0;

@@ -145,6 +145,19 @@ class DeviceScene:
                                              C.addressof(region), C.c_void_p(d_out), out_row_pitch,
                                              C.c_void_p(stream)))
 
+    def closest_hit(self, camera, rays7, seeds, mode=0):
+        """Test hook (pt_debug_closest_hit): the closest-hit scan of given rays -> (t, vector index or -1, generator after)."""
+        cam = camera if isinstance(camera, abi.pt_camera) else camera_c(camera)
+        rays7 = np.ascontiguousarray(rays7, dtype=np.float32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        n = rays7.shape[0]
+        t, idx, rng = np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros(n, np.uint32)
+        L = lib()
+        L.pt_debug_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(L.pt_debug_closest_hit(self._h, C.addressof(cam), n, rays7.ctypes.data, seeds.ctypes.data, mode, t.ctypes.data, idx.ctypes.data,
+                                      rng.ctypes.data))
+        return t, idx, rng
+
     def launch_count(self):
         n = C.c_uint64()
         _check(lib().pt_scene_launch_count(self._h, C.byref(n)))

@@ -52,6 +52,8 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
 }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __shfl_xor_sync(unsigned, T v, int) { return v; }  // a team of one
+inline unsigned __ballot_sync(unsigned, bool pred) { return pred ? 1u : 0u; }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 inline void sincos(double x, double* s, double* c) { *s = sin(x), *c = cos(x); }
 
 // work counters of the host build (PT_STAT is empty in the device build)

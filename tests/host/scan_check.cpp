@@ -23,7 +23,7 @@ namespace {
 struct HostScene {
   PackedScene ps;
   std::vector<unsigned char> blob_cull, blob_brute;
-  std::vector<int32_t> keys;
+  std::vector<int32_t> keys, object_id;
   SceneDesc cull {}, brute {};
 };
 
@@ -40,7 +40,7 @@ void fill_desc(const HostScene& h, const std::vector<unsigned char>& blob, Scene
   d.n_sphere_chunks = (uint32_t)ps.sphere_chunk_open.size(), d.n_moving_chunks = (uint32_t)ps.moving_chunk_open.size();
   d.sphere_aux = ps.sphere_aux.data(), d.moving_aux = ps.moving_aux.data(), d.rect_aux = ps.rect_aux.data();
   d.tri_aux = ps.tri_aux.data(), d.box_aux = ps.box_aux.data(), d.media = ps.media.data();
-  d.keys = h.keys.data();
+  d.keys = h.keys.data(), d.object_id = h.object_id.data();
   for (int k = 0; k < 6; ++k) d.key_base[k] = key_base[k];
   d.n_media_groups = ps.n_media_groups, d.n_flat_groups = ps.n_flat_groups, d.n_late_sphere_groups = ps.n_late_sphere_groups;
 }
@@ -223,18 +223,7 @@ int scan_check(const pt_scene* scene, const pt_camera* cam, int mode, uint64_t s
   }
   PackedScene& ps = h.ps;
   uint32_t key_base[6];
-  key_base[G_SPHERE] = (uint32_t)h.keys.size();
-  for (const auto& a : ps.sphere_aux) h.keys.push_back(a.key);
-  key_base[G_MOVING_SPHERE] = (uint32_t)h.keys.size();
-  for (const auto& a : ps.moving_aux) h.keys.push_back(a.key);
-  key_base[G_RECT] = (uint32_t)h.keys.size();
-  for (const auto& a : ps.rect_aux) h.keys.push_back(a.key);
-  key_base[G_TRIANGLE] = (uint32_t)h.keys.size();
-  for (const auto& a : ps.tri_aux) h.keys.push_back(a.key);
-  key_base[G_BOX] = (uint32_t)h.keys.size();
-  for (const auto& a : ps.box_aux) h.keys.push_back(a.key);
-  key_base[G_MEDIUM] = (uint32_t)h.keys.size();
-  for (const auto& a : ps.media) h.keys.push_back(a.key);
+  build_key_tables(ps, h.keys, key_base, h.object_id);
   h.keys.push_back(0);
 
   // brute force: no chunk boxes (the packer's default), no trees
@@ -284,14 +273,21 @@ int scan_check(const pt_scene* scene, const pt_camera* cam, int mode, uint64_t s
       g.next(), g.next();
       const int m = mode >= 0 ? mode : (int)(i % 5);
       const Ray ray = make_ray(*scene, *cam, m, g, scene_size);
-      Rng rng_a { (uint32_t)g.next() | 1u }, rng_b = rng_a;
+      const uint32_t seed0 = (uint32_t)g.next() | 1u;
+      Rng rng_a { seed0 }, rng_b { seed0 };
       const Best a = closest_hit<true>(h.cull, sv_cull, ray, rng_a, true, 0, 1);
       const unsigned long long tri_before = pt_host_stats.triangle_tests;
       const PtHostStats keep = pt_host_stats;
       const Best b = closest_hit<true>(h.brute, sv_brute, ray, rng_b, true, 0, 1);
       brute_tri += pt_host_stats.triangle_tests - tri_before;
       pt_host_stats = keep;
-      const bool same = a.id == b.id && (a.id < 0 || __float_as_uint(a.t) == __float_as_uint(b.t)) && rng_a.s == rng_b.s;
+      // ... and the reference's own scan, object by object in vector order: the (min t, max key) rule over groups re-ordered
+      // by kind must give the same winner whenever no NaN is in play
+      Rng rng_c { seed0 };
+      const Best c = closest_hit_in_order<true>(h.brute, sv_brute, ray, rng_c);
+      const bool nan_in_play = c.t != c.t || b.t != b.t;
+      const bool order_ok = nan_in_play || (c.id == b.id && (c.id < 0 || __float_as_uint(c.t) == __float_as_uint(b.t)) && rng_c.s == rng_b.s);
+      const bool same = order_ok && a.id == b.id && (a.id < 0 || __float_as_uint(a.t) == __float_as_uint(b.t)) && rng_a.s == rng_b.s;
       if (a.id >= 0) ++loc.hits;
       if (!same) {
         ++loc.mismatches;
@@ -300,7 +296,7 @@ int scan_check(const pt_scene* scene, const pt_camera* cam, int mode, uint64_t s
           have_bad = true;
           const float rr[7] = { ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.tm };
           std::memcpy(res.bad_ray, rr, sizeof rr);
-          res.t_cull = a.t, res.t_brute = b.t, res.id_cull = a.id, res.id_brute = b.id;
+          res.t_cull = order_ok ? a.t : c.t, res.t_brute = b.t, res.id_cull = order_ok ? a.id : c.id, res.id_brute = b.id;
         }
       }
     }
@@ -317,3 +313,25 @@ int scan_check(const pt_scene* scene, const pt_camera* cam, int mode, uint64_t s
 }
 
 }  // extern "C"
+
+// The rays of scan_check() (same generator, same seeds) for callers that trace them elsewhere -- the GPU ray-level
+// parity test feeds them to the CUDA scan and to the oracle's hit_world.
+extern "C" int scan_check_make_rays(const pt_scene* scene, const pt_camera* cam, int mode, uint64_t seed, uint64_t n_rays, float* rays7,
+                                    uint32_t* seeds) {
+  double scene_size = 1;
+  for (uint32_t i = 0; i < scene->n_triangles; ++i)
+    for (int k = 0; k < 3; ++k) scene_size = std::max(scene_size, (double)std::fabs(scene->triangles[i].v0[k]));
+  for (uint32_t i = 0; i < scene->n_spheres; ++i)
+    if (std::fabs(scene->spheres[i].radius) < 100)
+      for (int k = 0; k < 3; ++k) scene_size = std::max(scene_size, (double)std::fabs(scene->spheres[i].center0[k]));
+  for (uint64_t i = 0; i < n_rays; ++i) {
+    Xs g { seed * 0x9e3779b97f4a7c15ull + i * 0xbf58476d1ce4e5b9ull + 1ull };
+    g.next(), g.next();
+    const int m = mode >= 0 ? mode : (int)(i % 5);
+    const Ray ray = make_ray(*scene, *cam, m, g, scene_size);
+    const float rr[7] = { ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.tm };
+    std::memcpy(rays7 + 7 * i, rr, sizeof rr);
+    seeds[i] = (uint32_t)g.next() | 1u;
+  }
+  return 0;
+}

@@ -29,8 +29,8 @@ class Result(C.Structure):
                 ("tree_levels", C.c_int), ("tree_leaves", C.c_int), ("gtree_leaves", C.c_int)]
 
 
-@pytest.fixture(scope="session")
-def checker():
+def load_harness():
+    """Build (when stale) and load tests/host/scan_check.cpp."""
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-w",
@@ -38,6 +38,24 @@ def checker():
                                "-I" + os.path.join(ROOT, "path_tracer_b200", "csrc")] + SRC + ["-o", SO])
     lib = C.CDLL(SO)
     lib.scan_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.scan_check_make_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    return lib
+
+
+def make_rays(sc, cam, mode, seed, n):
+    """The harness's adversarial rays as arrays: ([n, 7] float32 {o, d, time}, [n] uint32 generator states)."""
+    lib = load_harness()
+    s, keep = sc.as_c()
+    c = camera_c(cam)
+    rays = np.zeros((n, 7), dtype=np.float32)
+    seeds = np.zeros(n, dtype=np.uint32)
+    assert lib.scan_check_make_rays(C.addressof(s), C.addressof(c), mode, seed, n, rays.ctypes.data, seeds.ctypes.data) == 0
+    return rays, seeds
+
+
+@pytest.fixture(scope="session")
+def checker():
+    lib = load_harness()
 
     def run(sc, cam, mode, seed, n_rays):
         s, keep = sc.as_c()

@@ -580,3 +580,25 @@ def test_resume_is_bit_identical_to_one_launch(c1, kernel):
         L.pt_debug_set_kernel(0)
     with pytest.raises(R.PathTracerError):
         R.render_resume(sc, cam, w, h, 5, 5, d, region, st_a)
+
+
+def test_staged_framebuffer_stores_are_invisible(c1):
+    """Finished pixels go through a float4 staging image and a coalescing resolve pass (16-byte stores); with the stage
+    off they are written straight into the caller's rows, three scalars each: same bits, both kernels, also for a tile
+    with a row pitch and for widths that are not a multiple of 4 (which always take the scalar path)."""
+    sc, cam, (w, h, _, d) = c1
+    L = R.lib()
+    try:
+        for kernel in (0, 1):
+            L.pt_debug_set_kernel(kernel)
+            for region in (abi.pt_region(0, 0, w, 64, 1), abi.pt_region(40, 100, 128, 32, 3), abi.pt_region(8, 8, 50, 20, 1)):
+                L.pt_debug_set_fb_stage(1)
+                a = R.render_region(sc, cam, w, h, 6, d, region)
+                launches = R.stats()["kernel_launches"]
+                L.pt_debug_set_fb_stage(0)
+                b = R.render_region(sc, cam, w, h, 6, d, region)
+                assert np.array_equal(_bits(a), _bits(b)), (kernel, region.w)
+                assert launches == R.stats()["kernel_launches"] + (1 if region.w % 4 == 0 else 0)
+    finally:
+        L.pt_debug_set_fb_stage(1)
+        L.pt_debug_set_kernel(0)
