@@ -678,6 +678,9 @@ __device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, 
 // assume no underflow or overflow in d . d (found by tests/host/scan_check.cpp: a direction of length 1e-23).
 // Out of line (it is rare: pixel (0, 0), whose generator returns zeros forever, and hand-made cameras).
 PT_DEV bool needs_in_order(const Ray& r) {
+#ifdef PT_NO_INORDER  // (experiments only)
+  return false;
+#endif
   const float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
   const float dmax = fmaxf(fmaxf(ax, ay), az), dmin = fminf(fminf(ax, ay), az);
   const float all = ((r.o.x + r.o.y) + r.o.z) + ((r.d.x + r.d.y) + r.d.z);  // (fminf / fmaxf drop a NaN: catch it here; inf - inf is NaN)

@@ -55,7 +55,8 @@ PT_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---------------------------------------------------------------- scene view
 // The kernels' view of the scan blob (in shared or global memory).  The arrays of the hot loops are plain pointers (the
 // compiler keeps them in registers across the phases; forming them from the descriptor's offsets at every use cost the
-// default scene 4 % -- measured); the flat groups' trees, used by few scenes, are formed where they are used.
+// default scene 4 %, 32-bit offsets from a common base 1 % -- measured); the flat groups' trees, used by few scenes,
+// are formed where they are used.
 struct SceneView {
   const Group* groups_;
   const float4 *sphere_, *moving_, *rect_, *triangle_, *box_, *sphere_box_, *moving_box_;

@@ -88,9 +88,6 @@ namespace {
 #ifndef PT_EXPRESS_POOL
 #define PT_EXPRESS_POOL 64
 #endif
-#ifndef PT_EXPRESS_RULE  // (calibrated on the BASELINE configs: tools/express_sweep.py)
-#define PT_EXPRESS_RULE(grid, share) (((grid) * 23 + 100) / 200)
-#endif
 #ifndef PT_WAVE_ITEMS
 #define PT_WAVE_ITEMS 4096
 #endif
@@ -105,7 +102,6 @@ constexpr int kWaveItems = PT_WAVE_ITEMS;                  // (ray, chunk) items
 constexpr int kWaveItemsStatic = kWaveItems * 3 / 8;       // ... of static spheres (from the front of the list)
 constexpr int kWaveItemsMoving = kWaveItems - kWaveItemsStatic;  // ... of moving spheres (from the back)
 constexpr unsigned long long kNoHit64 = 0x7f800000ffffffffull;  // {t = +inf, no object}
-constexpr unsigned long long kResolved64 = 0xffffffffffffffffull;  // the ray's scan was done in vector order (hit_t / hit_id hold it)
 #ifndef PT_FINE_RAYS
 #define PT_FINE_RAYS 160
 #endif
@@ -142,12 +138,14 @@ struct WavePool {
   int n_items_s, n_items_m;  // static / moving items reserved this round (may exceed what fits)
   int n_tgroups;   // flat groups with a tree in front of the first constant_medium (expanded breadth first: wave_tree_expand)
   int tgroups[kMaxTreeGroups];
+  unsigned long long express_positions;  // leading positions of the LPT order that belong to the express CTAs
   int heavy_rate;  // hand-off threshold of this frame (FrameTuning)
   int n_express;   // express CTAs of this frame
   int tree_passes; // tree passes per round: the deepest of those trees has this many levels above its leaves
   int tl_n[3], tl_off[3], tl_cap[3];  // the tree lists (in dynamic shared memory behind the staged scene): node items of pass 0 and 1, leaf items
   int free_count;
   int pixel_dry;   // the pixel queue has run dry
+  int in_order;    // a ray stored since the last BOXES phase needs the scan in vector order (store_ray)
   int service;     // hand-off service: 0 = keep polling, 1 = every producer is done and the queue is empty
   int blocks_ok;   // the sphere chunks fit the block table (else no short rounds)
   int n_blocks;    // fine BOXES: blocks of <= kFineBoxes chunks over all sphere groups (0: too many, coarse only)
@@ -275,6 +273,79 @@ __device__ __noinline__ unsigned long long wave_tree_expand(WavePool* W, uint2* 
 }
 }  // namespace
 
+// The whole scan of one ray by one thread, in group order (closest_hit, pt_prims.cuh): scenes with spheres behind a
+// constant_medium, and rounds in which a ray can meet a NaN.  Out of line (see wave_build_tables).
+template <bool kSmem, bool kTrees>
+__device__ __noinline__ void wave_sequential_scan(WavePool* W, const SceneDesc* scp, const unsigned char* blob_base, int slot) {
+  const SceneDesc& sc = *scp;
+  const SceneView sv = scene_view(sc, blob_base);
+  Ray ray;
+  ray.o = v3(W->ox[slot], W->oy[slot], W->oz[slot]);
+  ray.d = v3(W->dx[slot], W->dy[slot], W->dz[slot]);
+  ray.tm = W->tm[slot];
+  Rng rng { W->rng[slot] };
+  const Best best = closest_hit<kSmem, kTrees>(sc, sv, ray, rng, true, 0, 1);
+  W->hit_t[slot] = best.t, W->hit_id[slot] = best.id;
+  W->rng[slot] = rng.s;  // a constant_medium may have drawn from it (constant_medium.hpp:65)
+}
+
+// The CTA's tables, built once by one thread: the sphere chunks in blocks for the short rounds, the (ray, flat object)
+// units, the flat groups with a tree and the shares of the tree lists.  Out of line, like every RARE path of this
+// kernel: code that runs once per launch -- or never, for the scene at hand -- must not cost the hot loops registers
+// (measured: a dormant branch inlined into the kernel moved the default scene's frame by 3 %).
+template <bool kSmem, bool kTrees>
+__device__ __noinline__ void wave_build_tables(WavePool* W, const SceneDesc* scp, const Group* groups, const Tree* trees, unsigned int tree_list_bytes) {
+  const SceneDesc& sc = *scp;
+  const int n_groups = (int)sc.n_groups;
+  int nb = 0;
+  for (int gi = 0; gi < n_groups && nb >= 0; ++gi) {
+    const Group g = groups[gi];
+    if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
+    const int c_end = (g.begin + g.count) / kSphereChunk;
+    for (int cb = g.begin / kSphereChunk; cb < c_end; cb += kFineBoxes) {
+      if (nb == kMaxBoxBlocks) {
+        nb = -1;
+        break;
+      }
+      W->blocks[nb++] = make_int4(gi, cb, min(kFineBoxes, c_end - cb), 0);
+    }
+  }
+  W->n_blocks = nb < 0 ? 0 : nb, W->blocks_ok = nb >= 0;
+  // the flat objects in front of the first medium (as many as fit; the rest stays with the sequential part)
+  int nf = 0, nt = 0, late = n_groups;
+  for (int gi = 0; gi < n_groups; ++gi) {
+    const Group g = groups[gi];
+    const bool flat = g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX;
+    const bool tree = kTrees && flat && has_tree(sc, g);
+    if (g.type == G_MEDIUM || (flat && !tree && nf + 6 * g.count > kMaxFlats) || (tree && nt == kMaxTreeGroups)) {
+      late = gi;
+      break;
+    }
+    if (tree) {  // a group with a tree: traversed per ray in BOXES, its leaves become items
+      W->tgroups[nt++] = gi;
+      continue;
+    }
+    if (g.type == G_RECT || g.type == G_TRIANGLE)
+      for (int i = 0; i < g.count; ++i) W->flats[nf++] = make_int2(g.type, g.begin + i);
+    if (g.type == G_BOX)  // a box is six independent sides (box.hpp:20-25): the closest side is the box's hit
+      for (int i = 0; i < g.count; ++i)
+        for (int side = 0; side < 6; ++side) W->flats[nf++] = make_int2(G_BOX | (side << 8), g.begin + i);
+  }
+  W->n_flats = nf, W->first_late_group = late, W->n_tgroups = nt;
+  // the tree lists share what the launch left of the dynamic shared memory: node items of pass 0 / pass 1 / leaf items
+  int passes = 0;
+  for (int k = 0; k < nt; ++k) {
+    const Group g = groups[W->tgroups[k]];
+    passes = max(passes, trees[g.tree].levels - 1);
+    if (g.gtree >= 0) passes = max(passes, trees[g.gtree].levels - 1);
+  }
+  W->tree_passes = passes;
+  const int cap = (int)(tree_list_bytes / sizeof(uint2));
+  const int c0 = passes >= 1 ? cap / (passes == 1 ? 3 : 4) : 0, c1 = passes >= 2 ? cap / 4 : 0;
+  W->tl_off[0] = 0, W->tl_cap[0] = c0, W->tl_off[1] = c0, W->tl_cap[1] = c1, W->tl_off[2] = c0 + c1, W->tl_cap[2] = cap - c0 - c1;
+  W->tl_n[0] = W->tl_n[1] = W->tl_n[2] = 0;
+}
+
 // kTrees = false: the scene has no flat group with a tree (or culling is off) -- the tree paths are compiled out, so
 // that scenes without them (spheres and a handful of flats: the default scene) keep their registers and their
 // instruction-cache footprint.
@@ -322,20 +393,23 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   const SceneView sv = scene_view(sc, blob_base);
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
-  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rot = lane & (kSphereChunk - 1);
+  // (only what is cheap to keep: everything else that is loop invariant is re-formed where it is used -- the kernel runs at
+  // its register limit, and a value that is live across all phases costs more than the instruction that makes it)
+  const int tid = (int)threadIdx.x, lane = tid & 31;
   const pt_camera& cam = p.cam;
-  const float fwidth = (float)p.width, fheight = (float)p.height, fspp = (float)p.spp;
-  const unsigned lane_lt = (1u << lane) - 1u;
   const HeavyQueue& hq = p.heavy;
   // the frame's scheduling knobs: the cost probe's verdict when one ran (read from device memory: no host round trip),
   // else the launcher's defaults.  (The probe itself runs with n_express = 0 and no tuning.)
-  const int n_express = p.tuning ? min(__ldg(&p.tuning->n_express), (int)gridDim.x - 1) : p.n_express;
-  const int heavy_rate_frame = p.tuning ? __ldg(&p.tuning->heavy_rate) : kHeavyRate;
-  const unsigned long long express_positions = p.order_mode == 1 ? min((unsigned long long)n_express * (unsigned long long)kExpressPool, p.n_positions) : 0ull;
-  const bool express = (int)blockIdx.x < n_express;  // this CTA only serves the hand-off queue
+  // (kept in shared memory, not in registers that would be live across the whole kernel)
+  if (threadIdx.x == 0) {
+    const int n_express = p.tuning ? min(__ldg(&p.tuning->n_express), (int)gridDim.x - 1) : p.n_express;
+    W.n_express = n_express;
+    W.heavy_rate = p.tuning ? __ldg(&p.tuning->heavy_rate) : kHeavyRate;
+    W.express_positions = p.order_mode == 1 ? min((unsigned long long)n_express * (unsigned long long)kExpressPool, p.n_positions) : 0ull;
+  }
+  __syncthreads();
+  const bool express = (int)blockIdx.x < W.n_express;  // this CTA only serves the hand-off queue
   const bool sequential_scan = sc.n_late_sphere_groups != 0u;
-  const int n_groups = (int)sc.n_groups;
   unsigned int n_scans = 0;
 
   // Pull the next pixel of the queue; false (and the CTA-wide flag set) when the queue is dry.
@@ -347,12 +421,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       unsigned long long pos;
       if (express) {
         pos = atomicAdd(p.pixel_counter + 1, 1ull);
-        if (pos >= express_positions) {
+        if (pos >= W.express_positions) {
           atomicExch(&W.pixel_dry, 1);
           return false;
         }
       } else {
-        pos = express_positions + atomicAdd(p.pixel_counter, 1ull);
+        pos = W.express_positions + atomicAdd(p.pixel_counter, 1ull);
         if (pos >= p.n_positions) {
           atomicExch(&W.pixel_dry, 1);
           if (p.counters) atomicMin(p.counters + 2, globaltimer_ns());  // timeline: queue ran dry
@@ -427,7 +501,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         if (mo != 0u) atomicAdd(&W.n_own, __popc(mo));
       }
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (alive) W.list_a[base + __popc(m & lane_lt)] = (unsigned short)slot;
+      if (alive) W.list_a[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)slot;
     }
   };
   auto store_ray = [&](int slot, const Ray& ray, V3 att, V3 acc, Rng rng, int bounce, int sample) {
@@ -437,6 +511,12 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     W.acc_x[slot] = acc.x, W.acc_y[slot] = acc.y, W.acc_z[slot] = acc.z;
     W.rng[slot] = rng.s, W.bounce[slot] = bounce, W.sample[slot] = sample;
     W.best64[slot] = kNoHit64;
+    // A ray that can meet a NaN (pt_prims.cuh, "the scan in vector order") switches the CTA's NEXT round to the per-ray
+    // sequential scan -- closest_hit(), which knows what to do with it -- instead of burdening the phases with a test per
+    // ray: such rays are one in many millions.
+#ifndef PT_X1
+    if (needs_in_order(ray)) W.in_order = 1;
+#endif
   };
   auto load_ray = [&](int slot) -> Ray {
     Ray ray;
@@ -463,9 +543,9 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       } else {
         if (p.counters) atomicAdd(p.counters + 15, 1ull);  // stats: items scanned in place (tests check that it happens)
         if (moving)
-          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving(), sc.moving_aux, chunk, rot, ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
+          scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving(), sc.moving_aux, chunk, (lane & (kSphereChunk - 1)), ray, a, filter_a(a), f, G_MOVING_SPHERE, inl);
         else
-          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere(), sc.sphere_aux, chunk, rot, ray, a, filter_a(a), 0.f, G_SPHERE, inl);
+          scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere(), sc.sphere_aux, chunk, (lane & (kSphereChunk - 1)), ray, a, filter_a(a), 0.f, G_SPHERE, inl);
       }
       ++at;
     }
@@ -504,63 +584,15 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
   };
 
   int mode = 0;  // 0: this CTA's share of the pixel queue (none for an express CTA); 1: hand-off service
-  if (tid == 0) {
-    int nb = 0;
-    for (int gi = 0; gi < n_groups && nb >= 0; ++gi) {
-      const Group g = sv.groups()[gi];
-      if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
-      const int c_end = (g.begin + g.count) / kSphereChunk;
-      for (int cb = g.begin / kSphereChunk; cb < c_end; cb += kFineBoxes) {
-        if (nb == kMaxBoxBlocks) {
-          nb = -1;
-          break;
-        }
-        W.blocks[nb++] = make_int4(gi, cb, min(kFineBoxes, c_end - cb), 0);
-      }
-    }
-    W.n_blocks = nb < 0 ? 0 : nb, W.blocks_ok = nb >= 0;
-    // the flat objects in front of the first medium (as many as fit; the rest stays with the sequential part)
-    int nf = 0, nt = 0, late = n_groups;
-    for (int gi = 0; gi < n_groups; ++gi) {
-      const Group g = sv.groups()[gi];
-      const bool flat = g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX;
-      const bool tree = kTrees && flat && has_tree(sc, g);
-      if (g.type == G_MEDIUM || (flat && !tree && nf + 6 * g.count > kMaxFlats) || (tree && nt == kMaxTreeGroups)) {
-        late = gi;
-        break;
-      }
-      if (tree) {  // a group with a tree: traversed per ray in BOXES, its leaves become items
-        W.tgroups[nt++] = gi;
-        continue;
-      }
-      if (g.type == G_RECT || g.type == G_TRIANGLE)
-        for (int i = 0; i < g.count; ++i) W.flats[nf++] = make_int2(g.type, g.begin + i);
-      if (g.type == G_BOX)  // a box is six independent sides (box.hpp:20-25): the closest side is the box's hit
-        for (int i = 0; i < g.count; ++i)
-          for (int side = 0; side < 6; ++side) W.flats[nf++] = make_int2(G_BOX | (side << 8), g.begin + i);
-    }
-    W.n_flats = nf, W.first_late_group = late, W.n_tgroups = nt;
-    // the tree lists share what the launch left of the dynamic shared memory: node items of pass 0 / pass 1 / leaf items
-    int passes = 0;
-    for (int k = 0; k < nt; ++k) {
-      const Group g = sv.groups()[W.tgroups[k]];
-      passes = max(passes, sv.trees()[g.tree].levels - 1);
-      if (g.gtree >= 0) passes = max(passes, sv.trees()[g.gtree].levels - 1);
-    }
-    W.tree_passes = passes;
-    const int cap = (int)(p.tree_list_bytes / sizeof(uint2));
-    const int c0 = passes >= 1 ? cap / (passes == 1 ? 3 : 4) : 0, c1 = passes >= 2 ? cap / 4 : 0;
-    W.tl_off[0] = 0, W.tl_cap[0] = c0, W.tl_off[1] = c0, W.tl_cap[1] = c1, W.tl_off[2] = c0 + c1, W.tl_cap[2] = cap - c0 - c1;
-    W.tl_n[0] = W.tl_n[1] = W.tl_n[2] = 0;
-  }
+  if (tid == 0) wave_build_tables<kSmem, kTrees>(&W, &sc, sv.groups(), sv.trees(), p.tree_list_bytes);
   if (tid < 8) W.counts[tid] = 0;
-  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0;
+  if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0, W.in_order = 0;
   __syncthreads();
 
   if (!express) {  // (an express CTA goes straight to the hand-off service, whose first source is its reserved tiles)
     // ---- start: every pool slot (up to this CTA's fair share of the image) takes a pixel
     const int cap = p.pool_cap;
-    for (int s0 = warp * 32; s0 < kWavePool; s0 += kWaveThreads) {
+    for (int s0 = (tid >> 5) * 32; s0 < kWavePool; s0 += kWaveThreads) {
       const int slot = s0 + lane;
       bool alive = false;
       if (slot < cap) {
@@ -570,7 +602,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         V3 acc0;
         if (next_pixel(pixq, rng, px, py, acc0, sample0)) {
           Ray ray;
-          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
           store_ray(slot, ray, v3(1.f, 1.f, 1.f), acc0, rng, 0, sample0);
           W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;  // (an express CTA never hands a pixel off)
           alive = true;
@@ -618,7 +650,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           if (express && next_pixel(pixq, rng, px, py, acc0, sample0)) {
             const int slot = (int)W.free_list[atomicSub(&W.free_count, 1) - 1];
             Ray ray;
-            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
             store_ray(slot, ray, v3(1.f, 1.f, 1.f), acc0, rng, 0, sample0);
             W.pix[slot] = pixq, W.scans[slot] = -1;  // (never handed off again)
             W.list_a[atomicAdd(&W.n_next, 1)] = (unsigned short)slot;
@@ -697,15 +729,15 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 #endif
     if (mode == 1 && tid == 0 && p.counters) atomicAdd(p.counters + 8, 1ull), atomicAdd(p.counters + 9, (unsigned long long)n);  // stats
 
-    // ---- BOXES (or, with media in the scene, the whole sequential scan)
-    if (sequential_scan) {
+    // ---- BOXES (or, with spheres behind a medium -- or a ray that can meet a NaN in this round -- the whole sequential scan)
+#ifdef PT_X2
+    const bool seq_round = sequential_scan;
+#else
+    const bool seq_round = sequential_scan || W.in_order != 0;  // (W.in_order: stable since the barrier before `n` was read)
+#endif
+    if (seq_round) {
       for (int e = tid; e < n; e += kWaveThreads) {
-        const int slot = (int)W.list_a[e];
-        const Ray ray = load_ray(slot);
-        Rng rng { W.rng[slot] };
-        const Best best = closest_hit<kSmem, kTrees>(sc, sv, ray, rng, true, 0, 1);
-        W.hit_t[slot] = best.t, W.hit_id[slot] = best.id;
-        W.rng[slot] = rng.s;  // a constant_medium may have drawn from it (constant_medium.hpp:65)
+        wave_sequential_scan<kSmem, kTrees>(&W, &sc, blob_base, (int)W.list_a[e]);
       }
     } else {
       // one work unit = one ray x (all its chunks | a block of kFineBoxes chunks)
@@ -715,17 +747,6 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int slot = (int)W.list_a[e];
         const Ray ray = load_ray(slot);
         const int unit = fine ? w - e * units_per_ray : 0;
-        if (needs_in_order(ray)) {
-          // a ray that can meet a NaN (pt_prims.cuh): the reference's own scan, in vector order, here and now; ITEMS
-          // and LATE leave the ray alone
-          if (unit == 0) {
-            Rng rng { W.rng[slot] };
-            const Best best = closest_hit_in_order<kSmem>(sc, sv, ray, rng);
-            W.hit_t[slot] = best.t, W.hit_id[slot] = best.id, W.rng[slot] = rng.s;
-            W.best64[slot] = kResolved64;
-          }
-          continue;
-        }
         CullRay cr;
         const int cull_set = make_cull_ray(sc, ray, cr);
         const float a = vdot(ray.d, ray.d);  // sphere.hpp:69
@@ -737,7 +758,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           continue;
         }
         const int4 blk = fine ? W.blocks[unit] : make_int4(0, 0, 0, 0);
-        for (int gi = fine ? blk.x : 0; gi < (fine ? blk.x + 1 : n_groups); ++gi) {
+        for (int gi = fine ? blk.x : 0; gi < (fine ? blk.x + 1 : (int)sc.n_groups); ++gi) {
           const Group g = sv.groups()[gi];
           if (g.type != G_SPHERE && g.type != G_MOVING_SPHERE) continue;
           const bool moving = g.type == G_MOVING_SPHERE;
@@ -803,7 +824,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
     }
     __syncthreads();
-    if (kTrees && !sequential_scan) {
+    if (tid == 0) W.in_order = 0;  // (everybody has read it; SHADE and the next intake set it for the next round)
+    if (kTrees && !seq_round) {
       // ---- TREE PASSES: one level of the flat groups' trees per pass, one thread per (ray, node) item
       for (int pass = 0; pass < W.tree_passes; ++pass) {
         const int n_items = min(W.tl_n[pass], W.tl_cap[pass]);
@@ -815,7 +837,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     PT_PHASE(0)
 
     // ---- SPHERES: one thread per (ray, chunk) item, or per quarter of one
-    if (!sequential_scan) {
+    if (!seq_round) {
       const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving), n_f = kTrees ? min(W.tl_n[2], W.tl_cap[2]) : 0;
       const uint2* const leaf_items = tree_lists + W.tl_off[2];
 #ifdef PT_PHASE_TIMING
@@ -839,10 +861,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           const float a = vdot(ray.d, ray.d);
           Best b { kInf, -1 };
           if (moving)
-            scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving(), sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+            scan_chunk<kSmem, true, kSphereChunk, 1>(sc, sv.moving(), sc.moving_aux, (int)(it.x >> 10), (lane & (kSphereChunk - 1)), ray, a, filter_a(a),
                                                      __uint_as_float(it.y), G_MOVING_SPHERE, b);
           else
-            scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere(), sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a), 0.f,
+            scan_chunk<kSmem, false, kSphereChunk, 1>(sc, sv.sphere(), sc.sphere_aux, (int)(it.x >> 10), (lane & (kSphereChunk - 1)), ray, a, filter_a(a), 0.f,
                                                       G_SPHERE, b);
           if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
         }
@@ -868,10 +890,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             const float a = vdot(ray.d, ray.d);
             Best b { kInf, -1 };
             if (moving)
-              scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving(), sc.moving_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+              scan_chunk<kSmem, true, kFineQuarter, kParts>(sc, sv.moving(), sc.moving_aux, (int)(it.x >> 10), (lane & (kSphereChunk - 1)), ray, a, filter_a(a),
                                                             __uint_as_float(it.y), G_MOVING_SPHERE, b);
             else
-              scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere(), sc.sphere_aux, (int)(it.x >> 10), rot, ray, a, filter_a(a),
+              scan_chunk<kSmem, false, kFineQuarter, kParts>(sc, sv.sphere(), sc.sphere_aux, (int)(it.x >> 10), (lane & (kSphereChunk - 1)), ray, a, filter_a(a),
                                                              0.f, G_SPHERE, b);
             if (b.id >= 0) atomicMin(&W.best64[slot], pack_sphere_winner(moving ? sc.moving_aux : sc.sphere_aux, b));
           } else if (w >= f_base && w < f_base + n * n_flats) {
@@ -879,7 +901,6 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             const int2 fo = W.flats[j];
             const int slot = (int)W.list_a[(w - f_base) - j * n];
             const Ray ray = load_ray(slot);
-            if (needs_in_order(ray)) continue;  // (scanned in vector order in BOXES)
             Best b { kInf, -1 };
             if ((fo.x & 255) == G_BOX) {
               const float4 p0 = ld4<kSmem>(sv.box() + 2 * fo.y);
@@ -905,20 +926,17 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     for (int e = tid; e < n; e += kWaveThreads) {
       const int slot = (int)W.list_a[e];
       Best best;
-      if (sequential_scan) {
+      if (seq_round) {
         best.t = W.hit_t[slot], best.id = W.hit_id[slot];
       } else {
-        const unsigned long long w64 = W.best64[slot];
-        best = unpack_winner(sc, w64);
+        best = unpack_winner(sc, W.best64[slot]);
         const int late = W.first_late_group;
-        if (w64 == kResolved64) {  // scanned in vector order in BOXES, media included
-          best.t = W.hit_t[slot], best.id = W.hit_id[slot];
-        } else if (late < n_groups) {
+        if (late < (int)sc.n_groups) {
           // from the first constant_medium on, in group order against the running closest hit; a medium commits
           // unconditionally and may draw from the pixel's stream (constant_medium.hpp:52-65)
           const Ray ray = load_ray(slot);
           Rng rng { W.rng[slot] };
-          for (int gi = late; gi < n_groups; ++gi) {
+          for (int gi = late; gi < (int)sc.n_groups; ++gi) {
             const Group g = sv.groups()[gi];
             if (g.type == G_RECT || g.type == G_TRIANGLE || g.type == G_BOX) {
               if (kTrees && has_tree(sc, g))
@@ -955,8 +973,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       }
       unit_base[kWaveKinds] = units;
     }
-    const int heavy_rate = heavy_rate_frame;
-    for (int u = warp; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
+    const int heavy_rate = W.heavy_rate;
+    for (int u = tid >> 5; u < unit_base[kWaveKinds]; u += kWaveThreads / 32) {
       int kind = 0, e = 0, e_end = 0;
 #pragma unroll
       for (int k = 0; k < kWaveKinds; ++k)
@@ -987,10 +1005,10 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             if (p.order_mode == 2)
               p.probe_cost[pixq] = scans;  // cost probe: how deep did one sample of this pixel go
             else
-              pixel_finish(p, out_px, state_px, acc, rng, fspp);
+              pixel_finish(p, out_px, state_px, acc, rng, (float)p.spp);
             new_pixel = true;
           } else {
-            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
             att = v3(1.f, 1.f, 1.f);
             bounce = 0;
           }
@@ -1018,7 +1036,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           int px, py;
           alive = mode == 0 && next_pixel(pixq, rng, px, py, acc, sample);
           if (alive) {
-            camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+            camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
             att = v3(1.f, 1.f, 1.f);
             bounce = 0;
             W.pix[slot] = pixq, W.scans[slot] = express ? -1 : 0;
@@ -1068,7 +1086,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           float *unused, *state_px;
           queue_pixel(p, pixq, px, py, unused, state_px);
           pixel_start(p, px, py, state_px, rng, acc, sample);
-          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
           att = v3(1.f, 1.f, 1.f), bounce = 0, have = true;
         } else {
           // (2) the hand-off queue: lane 0 claims an entry, the lanes read one word each
@@ -1116,11 +1134,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
             int x, y;
             float *out_px, *state_px;
             queue_pixel(p, pixq, x, y, out_px, state_px);
-            pixel_finish(p, out_px, state_px, acc, rng, fspp);
+            pixel_finish(p, out_px, state_px, acc, rng, (float)p.spp);
           }
           have = false;
         } else {
-          camera_ray(cam, px, py, fwidth, fheight, rng, ray);
+          camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
           att = v3(1.f, 1.f, 1.f), bounce = 0;
         }
       }
@@ -1136,13 +1154,18 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 }
 
 // ---------------------------------------------------------------- LPT tile order
-// How many of `grid` CTAs only serve the hand-off queue.  Without a probe: 17 of 148 (measured best on the default
-// scene).  With one: by the share of the probed work that sits in pixels above four times the average.
-__host__ __device__ inline int express_ctas(int grid, int heavy_share_x1000) {
+// How many of `grid` CTAs only serve the hand-off queue.  The express CTAs exist for LATENCY: the deepest pixel of the
+// frame is a serial chain of  chain = spp x (scans per sample of a deep pixel ~ 0.6 x the deepest probed sample) x 9 us
+// (a short round), while the frame as a whole takes about  frame = spp x mean scans x pixels / (grid x 30 scans / us).
+// Where the chain is as long as the frame (the default scene: 800x480, ratio 1.2) 17 of 148 CTAs is the measured optimum;
+// where the frame is many chains long they only need to keep the queue from piling up, and every CTA they do not
+// take renders pixels.  Measured optima (tools/express_sweep.py): ratio 1.19 -> 17, 0.22 -> 8, 0.14 -> 2..4,
+// 0.055 -> 4..8, 0.02 -> 2..4 of 148; the rule below is 17/148 x sqrt(ratio), at least 2.  Without a probe: 17 of 148.
+__host__ __device__ inline int express_ctas(int grid, float chain_over_frame) {
   if (grid < 64) return 0;
-  int n = (grid * 23 + 100) / 200;
-  if (heavy_share_x1000 >= 0) n = PT_EXPRESS_RULE(grid, heavy_share_x1000);
-  return n < 1 ? 1 : (n > grid / 3 ? grid / 3 : n);
+  const float r = chain_over_frame < 0.f || chain_over_frame > 1.f ? 1.f : chain_over_frame;
+  const int n = (int)(0.1149f * (float)grid * sqrtf(r) + 0.5f);
+  return n < 2 ? 2 : n;
 }
 
 // One block: bin the tiles by probed cost (sum of the probes inside the tile), then list them from the
@@ -1201,7 +1224,8 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict_
     // a pixel is heavy when it spends more than four times the frame's average per sample (the default scene: 2.6 scans
     // per sample, rate 10); never below the default
     t.heavy_rate = max(kHeavyRate, (int)((4ull * sum + (unsigned long long)n_probes / 2ull) / (unsigned long long)max(n_probes, 1)));
-    t.n_express = n_express_forced >= 0 ? n_express_forced : express_ctas(grid, t.heavy_share_x1000);
+    const float chain_over_frame = 162.f * (float)grid * (float)deepest / (fmaxf(1e-3f * (float)t.mean_scans_x1000, 1e-3f) * (float)region_w * (float)region_h);
+    t.n_express = n_express_forced >= 0 ? n_express_forced : express_ctas(grid, chain_over_frame);
     t.pad[0] = t.pad[1] = t.pad[2] = 0;
     *tuning = t;
   }
@@ -1287,7 +1311,7 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     const unsigned long long share = (pixels + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
     q.pool_cap = (int)(share < 32ull ? 32ull : (share > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : share));
     // a few CTAs only serve the hand-off queue (short rounds for the deepest pixels of the image)
-    q.n_express = p.n_express >= 0 ? p.n_express : express_ctas(grid, -1);  // (a frame with a cost probe brings its own: FrameTuning)
+    q.n_express = p.n_express >= 0 ? p.n_express : express_ctas(grid, -1.f);  // (a frame with a cost probe brings its own: FrameTuning)
     if (q.n_express >= grid) q.n_express = grid - 1;
     if (p.order_mode == 2) {
       q.n_express = 0;

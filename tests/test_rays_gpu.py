@@ -36,8 +36,11 @@ def _compare(sc, cam, cport, mode, seed, n, what):
         exact = same_t & (i == want_i) & (rng == want_rng)
         bad = ~exact & ~medium
         assert not bad.any(), (what, name, int(bad.sum()), rays[bad][:3].tolist(), t[bad][:3], want_t[bad][:3], i[bad][:3], want_i[bad][:3])
-        soft = ~exact & medium  # a medium in play: same generator consumption or a different decision, a few per million
-        assert soft.sum() <= max(3, n // 2000), (what, name, int(soft.sum()))
+        # a medium in play: its t goes through log(), so the last bits may differ (same object, same generator state) ...
+        with np.errstate(invalid="ignore"):
+            close = (i == want_i) & (rng == want_rng) & (np.abs(t - want_t) <= 4e-6 * np.abs(want_t))
+        flipped = ~exact & medium & ~close  # ... and a handful per million decide differently whether the medium was hit
+        assert flipped.sum() <= max(3, n // 20000), (what, name, int(flipped.sum()))
     return int((want_i >= 0).sum())
 
 
@@ -95,3 +98,41 @@ def test_rectangle_plane_nan_is_the_references(cport):
             assert np.array_equal(np.isnan(t), np.isnan(want_t)) and np.array_equal(_bits(t)[~np.isnan(t)], _bits(want_t)[~np.isnan(t)])
     finally:
         ds.close()
+
+
+def test_render_level_nan_scenario(cport):
+    """The NaN quirk through the whole renderer.  Pixel (0,0) has seed 0, a generator that returns zeros forever, so its
+    Lambertian bounces add unit_vec = (-1, 0, -0) to the normal (rtweekend.hpp:60-67): off an xy rectangle the scattered
+    direction is (-1, 0, 1), d_y == 0 exactly.  An xz rectangle placed exactly at the height of that bounce point then has
+    t = 0/0 = NaN for the scattered ray -- accepted by the reference, poisoning its scan.  The wavefront kernel sees such
+    a ray when it is stored and runs that round through the per-ray sequential scan; the image must be the oracle's,
+    NaN for NaN, in both kernels."""
+    w, h, spp = 8, 6, 3
+
+    def build(k_y=None):
+        s = scenes.Scene()
+        s.rect(-20, 20, -20, 20, -1.0, s.lambertian((0.8, 0.7, 0.6)))                      # the wall the camera looks at
+        if k_y is not None:
+            s.rect(-30, 30, -0.9, 4.0, k_y, s.lambertian((0.2, 0.9, 0.2)), axis=abi.AXIS_XZ)  # the plane of the bounce
+        s.sphere((-3, 0, 2), 1.0, s.metal((0.9, 0.9, 0.9), 0.0))                          # listed after it: rejected by a NaN
+        s.triangle((-9, -9, 3.5), (9, -9, 3.5), (0, 9, 3.5), s.lambertian((0.3, 0.3, 0.9)))  # listed after it: accepted
+        return s
+
+    cam = scenes.make_camera((0, 0, 3), (0, 0, -1), (0, 1, 0), 40.0, w / h, 0.0, 4.0)
+    # the first bounce of pixel (0,0): u = v = 0 and a zero lens offset (seed 0)
+    ray0 = np.array(list(cam["origin"]) + list(np.float32(cam["lower_left_corner"]) - np.float32(cam["origin"])) + [0.0], dtype=np.float32)
+    out = cport.hit_scatter(build(), ray0, 0)
+    assert out[0] == 1.0 and out[11] == 1.0 and out[19] == 0.0, out  # hit, scattered, direction.y == 0 exactly
+    sc = build(k_y=float(out[16]))  # the xz rectangle exactly at the bounce point's height
+    t, idx, _ = cport.hit_world_batch(sc, np.array([list(out[15:21]) + [0.0]], np.float32), np.array([0], np.uint32))
+    assert np.isnan(t[0]), (t, idx)  # the reference's scan of the scattered ray is poisoned
+    want, _ = cport.render(sc, cam, w, h, spp, 50)
+    L = R.lib()
+    try:
+        for kernel in (0, 1):
+            L.pt_debug_set_kernel(kernel)
+            got = R.render(sc, cam, w, h, spp, 50)
+            same = (_bits(got) == _bits(want)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), (kernel, got[0, 0], want[0, 0], int((~same).sum()))
+    finally:
+        L.pt_debug_set_kernel(0)

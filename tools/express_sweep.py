@@ -22,6 +22,9 @@ for n in [int(a) for a in sys.argv[3:]] or [-1]:
         ms.append(ev0.elapsed_time(ev1))
     out = (C.c_ulonglong * 11)()
     L.pt_debug_timeline(ds._h, out)
+    tun = (C.c_int * 5)()
+    L.pt_debug_frame_tuning(ds._h, tun)
     print("%s express %3d: ms %s  (dry %.2f, done %.2f, regular CTAs out %.2f / %.2f ms, handed off %d, queue wait avg %.2f max %.2f ms) fb %.6f" % (
         workload, n, " ".join("%.2f" % m for m in ms), out[0] / 1e6, out[1] / 1e6, out[2] / 1e6, out[3] / 1e6, out[4],
         out[7] / max(out[4], 1) / 1e6, out[8] / 1e6, float(fb.mean())), flush=True)
+    print("      probe: heavy rate %d, express %d, mean %.2f scans/sample, heavy share %.3f, deepest sample %d" % (tun[0], tun[1], tun[2] / 1e3, tun[3] / 1e3, tun[4]), flush=True)
