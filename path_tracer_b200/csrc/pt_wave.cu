@@ -114,6 +114,10 @@ constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in ru
 constexpr int kMaxBoxBlocks = 64;
 constexpr int kMaxFlats = 256;
 constexpr int kMaxTreeGroups = 8;
+#ifndef PT_TREE_UNROLL
+#define PT_TREE_UNROLL 4
+#endif
+constexpr int kTreeUnroll = PT_TREE_UNROLL;  // node boxes tested per trip of a tree expansion's loop
 static_assert(kWavePool <= 1024, "an item packs the pool slot into 10 bits");
 
 struct WavePool {
@@ -248,7 +252,7 @@ __device__ __noinline__ unsigned long long wave_tree_expand(WavePool* W, uint2* 
   for (int c = first; c < first + count; c += 32) {
     const int k = min(32, first + count - c);
     uint32_t m = 0;
-#pragma unroll 1
+#pragma unroll kTreeUnroll  // (the boxes come from L2 when the scene is too large to stage: several loads in flight)
     for (int j = 0; j < k; ++j) m = __funnelshift_l(test(boxes + 2 * (c + j)), m, 1);
     if (m == 0u) continue;
     int at = atomicAdd(&W->tl_n[dest], __popc(m));
@@ -1332,6 +1336,11 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
       const unsigned long long sh = (q.n_positions + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
       q.pool_cap = (int)(sh < 32ull ? 32ull : (sh > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : sh));
     }
+#ifndef PT_TREE_POOL
+#define PT_TREE_POOL 640
+#endif
+    // (scenes with flat trees: fewer rays in flight, so that the (ray, node) and (ray, leaf) items of a round fit the tree lists)
+    if (trees && q.pool_cap > PT_TREE_POOL) q.pool_cap = PT_TREE_POOL;
     // pixel-order permutation pos -> (pos * scramble) mod pixels: a multiplier near pixels / golden ratio,
     // made coprime with the pixel count so that it is a bijection
     unsigned long long mul = (unsigned long long)((double)pixels * 0.6180339887498949) | 1ull;
