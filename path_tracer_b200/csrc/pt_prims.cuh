@@ -197,10 +197,49 @@ PT_DEV bool triangle_hit_t(const Ray& r, V3 v0, V3 e1, V3 e2, float tmin, float 
 
 PT_DEV V3 moving_center(V3 c0, V3 dv, float f) { return vadd(c0, vscale(f, dv)); }  // sphere.hpp:55
 
+// (ranges and helpers of the slab tests; "chunk culling" below explains them)
+constexpr float kCullInvMax = 1.152921504606847e18f;  // 2^60
+constexpr float kCullDirMin = 9.5367431640625e-7f;    // 2^-20
+constexpr float kCullDirMax = 1048576.f;              // 2^20
+PT_DEV float rcp_fast(float x) {
+#ifdef __CUDACC__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+// Can NO side of the box p0..p1 be hit anywhere on the ray's line (box.hpp:29-50 with min = -inf, max = +inf)?  A side's
+// hit passes the reference's own bounds check (rectangle.hpp:38-41), so its point lies on the box up to the rounding of
+// o + t d: the line then crosses the box grown by any margin above that rounding -- here a generous 1e-3 of the distances
+// involved.  true: provably no hit (the slab test of the grown box fails on the whole line); false: don't know.  Rays
+// outside the range the clamped reciprocal is good for answer "don't know".
+PT_DEV bool box_line_missed(const Ray& r, V3 p0, V3 p1) {
+  const float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
+  const float dmax = fmaxf(fmaxf(ax, ay), az), dmin = fminf(fminf(ax, ay), az);
+  const float lox = fminf(p0.x, p1.x), hix = fmaxf(p0.x, p1.x), loy = fminf(p0.y, p1.y), hiy = fmaxf(p0.y, p1.y);
+  const float loz = fminf(p0.z, p1.z), hiz = fmaxf(p0.z, p1.z);
+  const float far = (fmaxf(fabsf(r.o.x - lox), fabsf(r.o.x - hix)) + fmaxf(fabsf(r.o.y - loy), fabsf(r.o.y - hiy))) +
+                    fmaxf(fabsf(r.o.z - loz), fabsf(r.o.z - hiz));
+  const float m = 1.0e-3f * (far + ((fabsf(r.o.x) + fabsf(r.o.y)) + fabsf(r.o.z)));
+  if (!(dmin > 0.f && dmax >= kCullDirMin && dmax <= kCullDirMax && m - m == 0.f)) return false;  // (m: NaN / inf anywhere)
+  const float ix = fminf(fmaxf(rcp_fast(r.d.x), -kCullInvMax), kCullInvMax), iy = fminf(fmaxf(rcp_fast(r.d.y), -kCullInvMax), kCullInvMax);
+  const float iz = fminf(fmaxf(rcp_fast(r.d.z), -kCullInvMax), kCullInvMax);
+  const float x0 = (lox - m - r.o.x) * ix, x1 = (hix + m - r.o.x) * ix, y0 = (loy - m - r.o.y) * iy, y1 = (hiy + m - r.o.y) * iy;
+  const float z0 = (loz - m - r.o.z) * iz, z1 = (hiz + m - r.o.z) * iz;
+  const float t_in = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+  const float t_out = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+  return t_in > t_out;
+}
+
 // constant_medium.hpp:28-78.  Draws one RNG number iff both boundary hits
-// succeed and rec1.t < rec2.t after clipping.
-PT_DEV bool medium_hit_t(const MediumRec& m, const Ray& r, float tmin, float tmax, Rng& rng, float& t_out) {
+// succeed and rec1.t < rec2.t after clipping.  `shortcut`: prove the common case -- the ray's line misses the boundary
+// box altogether -- with one slab test instead of the twelve rectangle tests of the two boundary hits (off when culling
+// is off, so that the tests compare with and without it).
+PT_DEV bool medium_hit_t(const MediumRec& m, const Ray& r, float tmin, float tmax, Rng& rng, float& t_out, bool shortcut = true) {
   float t1, t2;
+  if (shortcut && m.boundary_kind != PT_BOUNDARY_SPHERE && box_line_missed(r, vld(m.p0), vld(m.p1))) return false;
   if (m.boundary_kind == PT_BOUNDARY_SPHERE) {
     V3 center = vld(m.c0);
     if (m.moving) center = moving_center(center, vld(m.dv), fdiv(fsub(r.tm, m.time0), m.den));
@@ -299,18 +338,6 @@ struct CullRay {
   float ix, iy, iz;  // clamped 1 / d
   float qx, qy, qz;  // -o * (1 / d)
 };
-constexpr float kCullInvMax = 1.152921504606847e18f;  // 2^60
-constexpr float kCullDirMin = 9.5367431640625e-7f;    // 2^-20
-constexpr float kCullDirMax = 1048576.f;              // 2^20
-PT_DEV float rcp_fast(float x) {
-#ifdef __CUDACC__
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-#else
-  return 1.0f / x;
-#endif
-}
 // Returns the box set of this ray.
 PT_DEV int make_cull_ray(const SceneDesc& sc, const Ray& r, CullRay& c) {
   const float dmax = fmaxf(fmaxf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z));
@@ -729,7 +756,7 @@ __device__ __noinline__ Best closest_hit_in_order(const SceneDesc* scp, const fl
         break;
       }
       default:
-        hit = medium_hit_t(sc.media[idx], r, kTMin, closest, *rng, t);
+        hit = medium_hit_t(sc.media[idx], r, kTMin, closest, *rng, t, false);
         break;
     }
     if (hit) closest = t, best.t = t, best.id = id;  // render.hpp:44-47
@@ -775,7 +802,7 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
         if (team_size > 1) team_merge(sc, best, team_size);
         if (act) {
           float t;
-          if (medium_hit_t(sc.media[g.begin], r, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
+          if (medium_hit_t(sc.media[g.begin], r, kTMin, best.t, rng, t, sc.flat_cull != 0u)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
         }
         break;
       }

@@ -949,7 +949,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
                 scan_flat_group<kSmem>(sc, sv, g, ray, g.begin, 1, best);
             } else if (g.type == G_MEDIUM) {
               float t;
-              if (medium_hit_t(sc.media[g.begin], ray, kTMin, best.t, rng, t)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
+              if (medium_hit_t(sc.media[g.begin], ray, kTMin, best.t, rng, t, sc.flat_cull != 0u)) best.t = t, best.id = make_id(G_MEDIUM, g.begin);
             }
           }
           W.rng[slot] = rng.s;
