@@ -581,6 +581,21 @@ int pt_debug_frame_tuning(pt_device_scene* scene, int out[5]) {
   return PT_OK;
 }
 
+// Test hook (not part of pt_abi.h): the device's transcendentals on host arrays (pt_kernel.h: launch_probe_math).
+int pt_debug_math(int kind, int n, const float* in, float* out) {
+  if (n < 0 || (n && (!in || !out))) return fail(PT_ERR_INVALID_ARGUMENT, "pt_debug_math: bad argument");
+  if (n == 0) return PT_OK;
+  const size_t n_in = (size_t)n * (kind == 4 ? 2 : 1);
+  float* d = nullptr;
+  PT_CUDA(cudaMalloc(&d, (n_in + (size_t)n) * sizeof(float)));
+  cudaError_t e = cudaMemcpy(d, in, n_in * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_probe_math(kind, n, d, d + n_in, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + n_in, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "pt_debug_math");
+  return PT_OK;
+}
+
 // Debug aid (not part of pt_abi.h): staged + resolved framebuffer stores on / off.
 int pt_debug_set_fb_stage(int on) {
   g_fb_stage_enabled = on;

@@ -6,10 +6,9 @@
 // into FMA except where the reference itself calls sycl::fma (vec.hpp:12).
 // The helpers below use the explicit round-to-nearest intrinsics, which nvcc
 // never fuses, so the property does not depend on -fmad=false (the build sets
-// it anyway).  Transcendentals (sin cos asin atan2 log pow) are evaluated in
-// binary64 and rounded once to binary32: the reference uses glibc's float
-// functions, which are not correctly rounded in a small fraction of inputs;
-// that is the only source of GPU-vs-CPU differences (tolerance in tests/).
+// it anyway).  Transcendentals (sin cos asin atan2 log pow) follow glibc's own
+// float algorithms operation by operation (pt_glibc_math.cuh), so the GPU
+// render is the reference's CPU render bit for bit.
 #ifndef PT_DEVICE_CUH
 #define PT_DEVICE_CUH
 
@@ -70,29 +69,55 @@ PT_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {
   return vadd(r_out_perp, r_out_parallel);
 }
 
-// ---- transcendentals: binary64 evaluation, one rounding to binary32 -------
+}  // namespace ptb
+#include "pt_glibc_math.cuh"
+namespace ptb {
+
+// ---- transcendentals: sin, cos, log, pow(x, 5), asin and atan2 are glibc's own algorithms, bit for bit
+// (pt_glibc_math.cuh): the reference's host calls sinf / cosf / logf / powf / asinf / atan2f, which are not correctly
+// rounded, so "binary64 and round once" differs from them in the last bit now and then -- enough to flip a
+// constant_medium's hit / pass decision or a dielectric's reflect / refract decision a few times per million.
+// Out-of-line (one copy in the kernel image; the scan loop must own the instruction cache) and by value (nothing
+// forced into local memory).
+#ifndef PT_MATH_BINARY64  // (experiments: the round-1 evaluation of all of them)
+static __device__ __noinline__ float t_sin(float x) { return g_sinf(x); }
+PT_DEV float t_cos(float x) { return g_cosf(x); }
+static __device__ __noinline__ float2 t_sincos2(float x) { return make_float2(g_sinf(x), g_cosf(x)); }
+#else
 static __device__ __noinline__ float t_sin(float x) { return __double2float_rn(sin((double)x)); }
 PT_DEV float t_cos(float x) { return __double2float_rn(cos((double)x)); }
-// Out-of-line (one copy in the kernel image; the scan loop must own the instruction
-// cache) and by value (nothing forced into local memory).
 static __device__ __noinline__ float2 t_sincos2(float x) {
   double ds, dc;
   sincos((double)x, &ds, &dc);
   return make_float2(__double2float_rn(ds), __double2float_rn(dc));
 }
+#endif
 PT_DEV void t_sincos(float x, float& s, float& c) {
   const float2 r = t_sincos2(x);
   s = r.x, c = r.y;
 }
+#ifndef PT_MATH_BINARY64
+static __device__ __noinline__ float t_asin(float x) { return g_asinf(x); }
+static __device__ __noinline__ float t_atan2(float y, float x) { return g_atan2f(y, x); }
+#else
 PT_DEV float t_asin(float x) { return __double2float_rn(asin((double)x)); }
 PT_DEV float t_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
+#endif
+#ifndef PT_MATH_BINARY64
+static __device__ __noinline__ float t_log(float x) { return g_logf(x); }
+#else
 static __device__ __noinline__ float t_log(float x) { return __double2float_rn(log((double)x)); }
-// pow(x, 5.0f) (material.hpp:65): x^5 by binary64 products (4 roundings at 2^-53)
-PT_DEV float t_pow5(float x) {
+#endif
+// pow(x, 5.0f) (material.hpp:65)
+#ifndef PT_MATH_BINARY64
+static __device__ __noinline__ float t_pow5(float x) { return g_pow5(x); }
+#else
+PT_DEV float t_pow5(float x) {  // x^5 by binary64 products (4 roundings at 2^-53)
   const double d = (double)x;
   const double d2 = d * d;
   return __double2float_rn(d2 * d2 * d);
 }
+#endif
 // fmod(x, 1.0f) (texture.hpp:140,143): exact, like every fmod
 PT_DEV float t_fmod1(float x) { return fsub(x, truncf(x)); }
 

@@ -101,6 +101,10 @@ cudaError_t launch_resolve_fb(const float* stage, int w, int h, float* out, long
 cudaError_t launch_probe_rays(const SceneDesc& scene, int n, const float* d_rays7, const uint32_t* d_seeds, int mode, float* d_t,
                               int32_t* d_index, uint32_t* d_rng, cudaStream_t stream);
 
+// Test hook: out[i] = f(in[i]) with the device's transcendentals (pt_device.cuh): kind 0 sin, 1 cos, 2 log, 3 asin,
+// 4 atan2(in[2 i], in[2 i + 1]), 5 pow(x, 5).
+cudaError_t launch_probe_math(int kind, int n, const float* d_in, float* d_out, cudaStream_t stream);
+
 int max_smem_blob_bytes(int device);
 cudaError_t launch_render(const RenderParams& p, int device, int grid_override, cudaStream_t stream,
                           LaunchInfo* info);

@@ -201,6 +201,26 @@ cudaError_t launch_probe_rays(const SceneDesc& scene, int n, const float* d_rays
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) probe_math_kernel(int kind, int n, const float* __restrict__ in, float* __restrict__ out) {
+  const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  float r;
+  switch (kind) {
+    case 0: r = t_sin(in[i]); break;
+    case 1: r = t_cos(in[i]); break;
+    case 2: r = t_log(in[i]); break;
+    case 3: r = t_asin(in[i]); break;
+    case 4: r = t_atan2(in[2 * i], in[2 * i + 1]); break;
+    default: r = t_pow5(in[i]); break;
+  }
+  out[i] = r;
+}
+cudaError_t launch_probe_math(int kind, int n, const float* d_in, float* d_out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  probe_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(kind, n, d_in, d_out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_lane(const RenderParams& p, int device, int grid_override, cudaStream_t stream, LaunchInfo* info) {
   int sms = 0;
   cudaError_t err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
