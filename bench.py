@@ -441,13 +441,16 @@ def main():
             counters = None
     flop_per_path = flops_per_path(counters) if counters else float("nan")
     achieved = value * 1e6 * flop_per_path / 1e12
-    traffic = executed = None
+    traffic = executed = issued = per_launch = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         prof = json.load(open(tpath))
         traffic = prof.get(args.workload)
+        per_launch = prof.get(args.workload + "_paths_per_launch", w * h_base * spp)
         if prof.get(args.workload + "_executed_flop_per_launch"):
-            executed = prof[args.workload + "_executed_flop_per_launch"] / prof.get(args.workload + "_paths_per_launch", w * h_base * spp)
+            executed = prof[args.workload + "_executed_flop_per_launch"] / per_launch
+        if prof.get(args.workload + "_thread_instructions_per_launch"):
+            issued = prof[args.workload + "_thread_instructions_per_launch"] / per_launch
     peak_total = peak_tflops * world
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps,
@@ -462,17 +465,30 @@ def main():
                 "ms_per_step": 1e3 * float(e2e_t[0]) / e2e_steps},
         "gpu_launches": int(run["launches"]),  # per step, all ranks: cost probe + tile sort + render kernel on each
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_total, "unit": "TFLOP/s",
-                     "frac": achieved / peak_total, "traffic": traffic, "flop_per_path": flop_per_path,
+                     "frac": achieved / peak_total, "traffic": traffic,
+                     # the ncu capture's launch (profiles/traffic.json): c3-c5 were captured at reduced spp
+                     "traffic_paths_per_launch": per_launch if traffic is not None else None,
+                     "flop_per_path": flop_per_path,
                      "peak_per_gpu": peak_tflops, "n_gpus": world,
                      # what the kernel really executes (ncu, profiles/traffic.json): culling skips most of the
                      # reference's brute-force tests, so `achieved` (ALGORITHMIC flops / time) is not an issue rate
                      "executed_flop_per_path": executed,
                      "executed_tflops": None if executed is None else value * 1e6 * executed / 1e12,
+                     "executed_frac": None if executed is None else value * 1e6 * executed / 1e12 / peak_total,
+                     # every thread instruction (ncu), against the lane-issue peak = SMs x 128 lanes x clock = half the
+                     # FFMA flop peak: what actually bounds this kernel
+                     "thread_inst_per_path": issued,
+                     "issue_frac": None if issued is None else value * 1e6 * issued / (0.5e12 * peak_total),
                      "peak_source": "%d x the FFMA micro-kernel rate measured in this run (%.0f MHz implied); "
                                     "MEASURED_PEAKS.json has no fp32 entry; `achieved` counts the reference's brute-force "
                                     "scan (every object for every ray), most of which culling skips" % (world, peak_mhz)},
         "cpu_baseline": cpu,
     }
+    if line["roofline"]["frac"] > 1.0:
+        line["roofline"]["note"] = ("frac > 1 is the order-preserving culling at work, not skipped work: W is the reference's "
+                                    "brute-force scan (SURVEY.md 8(d): reported unchanged when a culling structure is used) and "
+                                    "the kernel reaches the same pixels, bit for bit and with equal scan counts (tests), while "
+                                    "testing a fraction of the objects; executed_frac / issue_frac are the hardware's view")
     if strong is not None:
         line["strong"] = strong
     if single is not None:

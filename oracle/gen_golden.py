@@ -11,7 +11,8 @@ unmodified reference code compiled in place:
   ref_renders.npz      linear fp32 framebuffers of small renders by libptref.so
                        (render_pixel<> of render.hpp:25-106, executor seeding :130-133)
   ref_hashes.json      sha256 of larger reference framebuffers (incl. the survey's
-                       800x480x32 hash of the default scene)
+                       800x480x32 hash of the default scene) and of the USE_SINGLE_TASK
+                       executor's images (oracle/_ref/libptref_st.so)
 """
 import gzip
 import hashlib
@@ -33,6 +34,7 @@ import scenes  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SMALL = [(64, 48, 4, 50), (64, 48, 16, 3), (33, 17, 5, 7)]
+SINGLE_TASK_CASES = [("c1", 64, 48, 4), ("c1", 200, 120, 4), ("shapes", 64, 48, 4), ("media", 64, 48, 4)]  # = tests/test_oracle.py
 
 
 def main(full=False):
@@ -77,6 +79,21 @@ def main(full=False):
             old = json.load(open(path))
             if "c1_800x480x32x50_render_full" in old:
                 hashes["c1_800x480x32x50_render_full"] = old["c1_800x480x32x50_render_full"]
+    # the reference's USE_SINGLE_TASK executor (render.hpp:113-122): ref_driver.cpp compiled with -DUSE_SINGLE_TASK
+    st_path = os.path.join(HERE, "_ref", "libptref_st.so")
+    if os.path.exists(st_path):
+        st = Ref(st_path)
+        for name, w, h, spp in SINGLE_TASK_CASES:
+            if name == "c1":
+                sc, cam = c1, c1cam
+            else:
+                sc, cam = scenes.ALL[name](w / h)
+            img = st.render_full(sc, cam, w, h, spp, nthreads=1)
+            hashes["single_task_%s_%dx%dx%dx50" % (name, w, h, spp)] = hashlib.sha256(img.tobytes()).hexdigest()
+    else:
+        path = os.path.join(GOLDEN, "ref_hashes.json")
+        if os.path.exists(path):
+            hashes.update({k: v for k, v in json.load(open(path)).items() if k.startswith("single_task_")})
     with open(os.path.join(GOLDEN, "ref_hashes.json"), "w") as f:
         json.dump(hashes, f, indent=1)
     print("golden: %d renders, hashes %s" % (len(renders), sorted(hashes)))

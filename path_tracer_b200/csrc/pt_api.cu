@@ -73,6 +73,8 @@ struct pt_device_scene {
   FrameTuning* last_tuning = nullptr;  // device: what the last cost probe said (pt_debug_frame_tuning)
   float* fb_stage = nullptr;  // float4 staging image of the last region size (pt_kernel.h: launch_resolve_fb)
   size_t fb_stage_bytes = 0;
+  uint2* tree_spill = nullptr;  // scenes with flat trees: the tree lists' continuation in global memory (pt_wave.cu)
+  size_t tree_spill_bytes = 0;
   int next_slot = 0;
   unsigned int kernel_launches = 0;  // kernels launched since creation (probe, tile sort, render)
   unsigned long long paths_launched = 0;
@@ -227,6 +229,7 @@ int upload(const pt_scene* scene, int device, pt_device_scene** out, double* h2d
   d.off_groups = ps.off_groups, d.off_sphere = ps.off_sphere, d.off_moving = ps.off_moving;
   d.off_rect = ps.off_rect, d.off_triangle = ps.off_triangle, d.off_box = ps.off_box;
   d.off_trees = ps.off_trees, d.off_nodes = ps.off_nodes, d.off_tree_ids = ps.off_tree_ids, d.n_trees = ps.n_trees;
+  d.off_planes = ps.off_planes, d.n_planes[0] = ps.n_planes[0], d.n_planes[1] = ps.n_planes[1], d.n_planes[2] = ps.n_planes[2];
   d.flat_extent = ps.flat_extent;
   d.n_objects = ps.n_objects;
   d.sphere_aux = reinterpret_cast<const SphereAux*>(ds->arena + o_saux);
@@ -340,6 +343,7 @@ void pt_scene_free(pt_device_scene* s) {
   cached_free(s->device, s->arena, s->arena_bytes);
   cached_free(s->device, s->lpt_buf, s->lpt_ints * sizeof(int));
   cached_free(s->device, s->fb_stage, s->fb_stage_bytes);
+  cached_free(s->device, s->tree_spill, s->tree_spill_bytes);
   delete s;
 }
 
@@ -397,6 +401,20 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
     }
     p.out = scene->fb_stage, p.out_row_pitch = 4ll * region->w, p.out_pixel_floats = 4;
   }
+  p.tree_spill = nullptr, p.tree_spill_cap = 0;
+  if (scene->desc.n_trees != 0u && g_kernel_kind == 0) {
+    // a ray that runs along a mesh crosses hundreds of leaves: what the shared-memory tree lists cannot hold continues here
+    const size_t need = (size_t)wave_grid(scene->device) * kTreeSpillLists * kTreeSpillCap * sizeof(uint2);
+    if (need > scene->tree_spill_bytes) {
+      cached_free(scene->device, scene->tree_spill, scene->tree_spill_bytes);
+      scene->tree_spill = nullptr, scene->tree_spill_bytes = 0;
+      void* buf = nullptr;
+      size_t got = 0;
+      PT_CUDA(cached_malloc(scene->device, &buf, need, &got));
+      scene->tree_spill = static_cast<uint2*>(buf), scene->tree_spill_bytes = got;
+    }
+    p.tree_spill = scene->tree_spill, p.tree_spill_cap = kTreeSpillCap;
+  }
   p.state = d_state, p.state_row_pitch = state_row_pitch, p.spp_from = spp_from;
   p.counters = scene->counters;
   p.team_size = g_team_size_override;  // 0 = chosen from the pixel count at launch
@@ -421,9 +439,12 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   PT_CUDA(cudaMemsetAsync(p.counters + 8, 0, 16 * sizeof(unsigned long long), st));  // hand-off service statistics
 
   // Longest-processing-time-first pixel order (wavefront kernel, images worth it): a cost probe traces
-  // ONE throw-away sample through every second pixel of every second row (1/(4 spp) of the frame's
-  // work), the tiles are sorted by probed cost, and the frame starts with the most expensive tiles so
-  // that the deepest pixels have the whole frame to finish and the cheapest ones fill its end.
+  // throw-away samples through every second pixel of every second row, the tiles are sorted by probed cost, and
+  // the frame starts with the most expensive tiles so that the deepest pixels have the whole frame to finish and
+  // the cheapest ones fill its end.  ONE probe sample per 64 samples of the frame (1 .. 8; 1/256 of the frame's work
+  // at most): a pixel that is deep in some of its samples only (the mesh: isolated pixels averaging 24 scans a sample
+  // where the mean is 2.3) shows in one probe sample with probability 1/2, and every such pixel that the order misses
+  // starts late and ends the frame with its whole serial chain.
   const unsigned long long pixels = (unsigned long long)region->w * (unsigned long long)region->h;
   if (g_lpt_enabled && pixels >= 32768ull && spp - spp_from >= 8) {
     const int pw = (region->w + kProbeStep - 1) / kProbeStep, ph = (region->h + kProbeStep - 1) / kProbeStep;
@@ -442,7 +463,12 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
     int* scratch = tile_order + (size_t)tiles_x * tiles_y;
     FrameTuning* tuning = reinterpret_cast<FrameTuning*>(scratch + (size_t)tiles_x * tiles_y);
     RenderParams probe = p;
-    probe.order_mode = 2, probe.probe_cost = probe_cost, probe.spp = 1, probe.spp_from = 0, probe.state = nullptr, probe.counters = nullptr;
+#ifdef PT_PROBE_SPP  // (experiments)
+    const int probe_spp = PT_PROBE_SPP;
+#else
+    const int probe_spp = std::min(std::max((spp - spp_from) / 64, 1), 8);
+#endif
+    probe.order_mode = 2, probe.probe_cost = probe_cost, probe.spp = probe_spp, probe.spp_from = 0, probe.state = nullptr, probe.counters = nullptr;
     probe.kernel_kind = 0;  // the probe always runs on the wavefront kernel
     probe.pixel_counter = next_queue_head();
     probe.heavy.stamp = ++scene->launch_stamp;
@@ -451,7 +477,7 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
     cudaError_t pe = launch_render(probe, scene->device, 0, st, nullptr);
     if (pe != cudaSuccess) return cuda_fail(pe, "cost probe launch");
     pe = launch_tile_order(probe_cost, region->w, region->h, tiles_x, tiles_y, tile_order, scratch, tuning, wave_grid(scene->device),
-                           g_n_express, st);
+                           g_n_express, probe_spp, st);
     if (pe != cudaSuccess) return cuda_fail(pe, "tile order launch");
     p.order_mode = 1, p.tile_order = tile_order, p.tiles_x = tiles_x, p.tiles_y = tiles_y;
     p.tuning = g_kernel_kind == 0 ? tuning : nullptr;
@@ -629,6 +655,15 @@ int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[11]) {
   out[2] = v[5] - v[1], out[3] = v[6] - v[1];  // first / last CTA out of regular work
   out[4] = v[7];                               // heavy pixels handed to the express lane
   out[5] = v[8], out[6] = v[9], out[7] = v[12], out[8] = v[13], out[9] = v[14], out[10] = v[15];
+  if (std::getenv("PT_LAST_PIXEL")) {  // -DPT_LAST_PIXEL builds
+    unsigned long long w = 0;
+    PT_CUDA(cudaMemcpy(&w, scene->counters + 16, sizeof w, cudaMemcpyDeviceToHost));
+    unsigned long long n_in_order = 0;
+    PT_CUDA(cudaMemcpy(&n_in_order, scene->counters + 17, sizeof n_in_order, cudaMemcpyDeviceToHost));
+    std::fprintf(stderr, "rays stored that ask for the vector-order scan: %llu\n", n_in_order);
+    std::fprintf(stderr, "last pixel: finished %.2f ms after the start, own %llu, service mode %llu, about %llu scans (rounds, if taken over)\n",
+                 (double)(w >> 24) / 1e6, (w >> 23) & 1ull, (w >> 22) & 1ull, (w & ((1ull << 22) - 1)) << 2);
+  }
   if (const char* env = std::getenv("PT_PHASE_TIMING")) {  // debug builds (-DPT_PHASE_TIMING): cycles per phase
     (void)env;
     std::fprintf(stderr, "desc: groups %u media %u flat %u sphere chunks %u moving chunks %u blob %u B\n", scene->desc.n_groups,

@@ -66,6 +66,8 @@ struct RenderParams {
   int pool_cap;                       // wavefront kernel: pixels a CTA may hold (set by the launcher)
   unsigned int staged_bytes;          // wavefront kernel: bytes of the arena kept in shared memory (set by the launcher)
   unsigned int tree_list_bytes;       // wavefront kernel: dynamic shared memory behind them for the tree lists (set by the launcher)
+  uint2* tree_spill;                  // wavefront kernel: global-memory continuation of the tree lists, kTreeSpillLists x tree_spill_cap items per CTA (null: none)
+  unsigned int tree_spill_cap;
   int n_express;                      // wavefront kernel: CTAs that only serve the hand-off queue (< 0 = automatic)
   const FrameTuning* tuning;          // wavefront kernel: the cost probe's verdict (null: no probe ran; the defaults apply)
   // pixel order of the wavefront kernel (queue position -> pixel)
@@ -84,11 +86,16 @@ struct LaunchInfo {
 };
 
 constexpr int kTile = 8;   // LPT ordering granularity (pixels)
-constexpr int kProbeStep = 2;  // the cost probe traces every kProbeStep-th pixel of every kProbeStep-th row
+constexpr int kTreeSpillLists = 3;       // node items of tree pass 0, of pass 1, leaf items
+constexpr unsigned int kTreeSpillCap = 32768;  // items per list and CTA beyond shared memory before a thread walks its subtree in place
+#ifndef PT_PROBE_STEP
+#define PT_PROBE_STEP 2
+#endif
+constexpr int kProbeStep = PT_PROBE_STEP;  // the cost probe traces every kProbeStep-th pixel of every kProbeStep-th row
 
 // Sort the region's tiles by probed cost, heaviest first (one small kernel).  `scratch` holds n_tiles ints.
 cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
-                              int* tile_order, int* scratch, FrameTuning* tuning, int grid, int n_express_forced, cudaStream_t stream);
+                              int* tile_order, int* scratch, FrameTuning* tuning, int grid, int n_express_forced, int probe_spp, cudaStream_t stream);
 int wave_grid(int device);  // CTAs of a wavefront launch on this device
 
 // The staged framebuffer {r, g, b, -} x (w x h) -> the caller's packed float3 rows, whole 16-byte stores, coalesced

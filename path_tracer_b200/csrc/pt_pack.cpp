@@ -551,6 +551,7 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
 
   Builder b(out);
   Segment seg;
+  std::vector<float> planes[3];  // plane coordinates of rectangles, box sides and media boundary boxes, per component
   for (uint32_t i = 0; i < sc.n_hittables; ++i) {
     const pt_order_entry e = sc.order[i];
     switch (e.kind) {
@@ -599,6 +600,7 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
         float axis_bits;
         const int32_t axis = r.axis;
         std::memcpy(&axis_bits, &axis, 4);
+        planes[2 - r.axis].push_back(r.k);  // xy: k is z, xz: y, yz: x (rectangle.hpp:50,88,126)
         seg.rect.push_back(f4 { r.a0, r.a1, r.b0, r.b1 });
         seg.rect.push_back(f4 { r.k, axis_bits, 0.f, 0.f });
         seg.rect_aux.push_back(ObjAux { r.material, (int32_t)i });
@@ -629,6 +631,7 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
           return PT_ERR_INVALID_ARGUMENT;
         }
         const pt_box& bx = sc.boxes[e.index];
+        for (int k = 0; k < 3; ++k) planes[k].push_back(bx.p0[k]), planes[k].push_back(bx.p1[k]);
         seg.box.push_back(f4 { bx.p0[0], bx.p0[1], bx.p0[2], 0.f });
         seg.box.push_back(f4 { bx.p1[0], bx.p1[1], bx.p1[2], 0.f });
         seg.box_aux.push_back(ObjAux { bx.material, (int32_t)i });
@@ -660,6 +663,7 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
           }
           const pt_box& bx = sc.boxes[m.boundary_index];
           for (int k = 0; k < 3; ++k) r.p0[k] = bx.p0[k], r.p1[k] = bx.p1[k];
+          for (int k = 0; k < 3; ++k) planes[k].push_back(bx.p0[k]), planes[k].push_back(bx.p1[k]);
         } else {
           error = "pt_scene: unknown medium boundary kind";
           return PT_ERR_INVALID_ARGUMENT;
@@ -700,6 +704,18 @@ int pack_scene(const pt_scene& sc, PackedScene& out, std::string& error) {
   out.off_nodes = append(out.blob, b.nodes.data(), b.nodes.size() * sizeof(f4));
   out.off_tree_ids = append(out.blob, b.tree_ids.data(), b.tree_ids.size() * sizeof(f4));
   out.n_trees = (uint32_t)b.trees.size();
+  {
+    std::vector<float> all;
+    for (int k = 0; k < 3; ++k) {
+      std::vector<float>& v = planes[k];
+      v.erase(std::remove_if(v.begin(), v.end(), [](float x) { return x != x; }), v.end());  // (a NaN plane equals nothing)
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+      out.n_planes[k] = (uint32_t)v.size();
+      all.insert(all.end(), v.begin(), v.end());
+    }
+    out.off_planes = append(out.blob, all.data(), all.size() * sizeof(float));
+  }
   out.flat_extent = (float)b.flat_extent;
   {
     // until compute_cull_boxes() has run for a camera, every chunk is scanned

@@ -23,6 +23,7 @@ struct PackedScene {
   uint32_t n_groups = 0;
   uint32_t off_groups = 0, off_sphere = 0, off_moving = 0, off_rect = 0, off_triangle = 0, off_box = 0;
   uint32_t off_trees = 0, off_nodes = 0, off_tree_ids = 0, n_trees = 0;
+  uint32_t off_planes = 0, n_planes[3] = { 0, 0, 0 };  // sorted plane coordinates per axis (pt_packed.h: SceneDesc::off_planes)
   float flat_extent = 0.f;
   uint32_t off_sphere_box = 0, off_moving_box = 0;  // [kCullSets][chunks][2] float4 each, "no culling" until set
   std::vector<SphereGeo> sphere_geo, moving_geo;    // indexed like sphere_aux / moving_aux

@@ -137,6 +137,10 @@ struct SceneDesc {
   uint32_t n_groups;
   uint32_t off_groups, off_sphere, off_moving, off_rect, off_triangle, off_box;
   uint32_t off_trees, off_nodes, off_tree_ids, n_trees;  // flat groups' trees: Tree[], float4 node boxes, float4 grazing-index leaves
+  // the coordinates k of every axis-aligned plane that carries a rectangle, a box side or a side of a medium's boundary box:
+  // n_planes[c] sorted floats for component c (x, y, z), one after the other.  A ray with d_c == 0 that starts ON such a
+  // plane has t = 0/0 there (pt_prims.cuh: needs_in_order)
+  uint32_t off_planes, n_planes[3];
   uint32_t flat_cull;         // 0: ignore the trees (every flat object is tested: pt_debug_set_cull(0))
   float flat_extent;          // max |coordinate| over the flat objects under a tree (the slab test's rounding allowance)
   uint32_t n_objects;         // reference n_hittables (for work accounting)

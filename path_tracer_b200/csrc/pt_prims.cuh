@@ -704,14 +704,32 @@ __device__ __noinline__ Best scan_flat_tree(KeyTable sc, FlatTrees ft, Group g, 
 // So are rays whose direction is outside [2^-20, 2^20]: the error bounds behind the miss filter and the box tests
 // assume no underflow or overflow in d . d (found by tests/host/scan_check.cpp: a direction of length 1e-23).
 // Out of line (it is rare: pixel (0, 0), whose generator returns zeros forever, and hand-made cameras).
-PT_DEV bool needs_in_order(const Ray& r) {
+// Does the ray with d_c == 0 start ON a plane that carries a rectangle / box side (SceneDesc::off_planes)?  Out of line: once
+// in millions of rays.
+static __device__ __noinline__ bool on_a_plane(const SceneDesc* sc, const unsigned char* blob_base, int c, float o_c) {
+  const float* v = reinterpret_cast<const float*>(blob_base + sc->off_planes);
+  int first = 0;
+  for (int k = 0; k < c; ++k) first += (int)sc->n_planes[k];
+  const int n = (int)sc->n_planes[c];
+  for (int i = 0; i < n; ++i)
+    if (v[first + i] == o_c) return true;
+  return false;
+}
+PT_DEV bool needs_in_order(const SceneDesc& sc, const unsigned char* blob_base, const Ray& r) {
 #ifdef PT_NO_INORDER  // (experiments only)
   return false;
 #endif
   const float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
   const float dmax = fmaxf(fmaxf(ax, ay), az), dmin = fminf(fminf(ax, ay), az);
   const float all = ((r.o.x + r.o.y) + r.o.z) + ((r.d.x + r.d.y) + r.d.z);  // (fminf / fmaxf drop a NaN: catch it here; inf - inf is NaN)
-  return !(dmin > 0.f && dmax >= kCullDirMin && dmax <= kCullDirMax && all - all == 0.f);
+  if (dmin > 0.f && dmax >= kCullDirMin && dmax <= kCullDirMax && all - all == 0.f) return false;  // (all but one ray in millions)
+  if (!(dmax >= kCullDirMin && dmax <= kCullDirMax && all - all == 0.f)) return true;
+  // a zero component: the only NaN a finite ray can meet is t = (k - o_c) / d_c = 0 / 0 on a plane it starts on; off every
+  // plane t is +-inf, the hit point's other coordinates are +-inf and the rectangle's bounds reject it -- unless a SECOND
+  // component is zero too (inf x 0 = NaN passes the bounds, rectangle.hpp:38-41)
+  const int zeros = (ax == 0.f) + (ay == 0.f) + (az == 0.f);
+  if (zeros != 1) return true;
+  return ax == 0.f ? on_a_plane(&sc, blob_base, 0, r.o.x) : ay == 0.f ? on_a_plane(&sc, blob_base, 1, r.o.y) : on_a_plane(&sc, blob_base, 2, r.o.z);
 }
 template <bool kSmem>
 __device__ __noinline__ Best closest_hit_in_order(const SceneDesc* scp, const float4* sphere, const float4* moving, const float4* rect,
@@ -775,7 +793,7 @@ PT_DEV Best closest_hit(const SceneDesc& sc, const SceneView& sv, const Ray& r, 
                         int team_size) {
   // a ray that can meet a NaN is scanned in vector order (above) by every member of its team, AFTER the team has
   // ridden along here without a ray: the other teams of the warp need it for their full-warp shuffles
-  const bool in_order = act && needs_in_order(r);
+  const bool in_order = act && needs_in_order(sc, sv.base, r);
   act = act && !in_order;
   Best best { kInf, -1 };
   const float a = vdot(r.d, r.d);  // sphere.hpp:69, loop invariant

@@ -20,6 +20,7 @@
 //     sit on a serial critical path) are traced by EXPRESS CTAs in short rounds, from the head of a
 //     longest-processing-time-first pixel order and from a global hand-off queue.
 // All arithmetic follows the operation order of the reference; see pt_device.cuh for the numerics contract.
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -111,14 +112,34 @@ constexpr int kFineRays = PT_FINE_RAYS;  // at most this many rays in the round:
 #endif
 constexpr int kFineBoxes = PT_FINE_BOXES;            // ... BOXES: a ray's chunks in blocks of this many
 constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in runs of this many
+#ifndef PT_QUEUE_PER_EXPRESS
+#define PT_QUEUE_PER_EXPRESS 16
+#endif
+constexpr int kQueuePerExpress = PT_QUEUE_PER_EXPRESS;  // waiting pixels per express CTA beyond which nobody hands off
+constexpr int kHandoffPause = 8;
 constexpr int kMaxBoxBlocks = 64;
 constexpr int kMaxFlats = 256;
 constexpr int kMaxTreeGroups = 8;
 #ifndef PT_TREE_UNROLL
 #define PT_TREE_UNROLL 4
 #endif
+#ifndef PT_LEAF_SUB
+#define PT_LEAF_SUB 1
+#endif
 constexpr int kTreeUnroll = PT_TREE_UNROLL;  // node boxes tested per trip of a tree expansion's loop
 static_assert(kWavePool <= 1024, "an item packs the pool slot into 10 bits");
+
+// What the out-of-line tree code needs of the kernel's context.  It lives in shared memory because the arguments of a
+// __noinline__ function beyond a few words travel through LOCAL memory: with the key table, the tree pointers, the group
+// and the ray passed by value the mesh frame moved 4.4 G local-memory sectors, and half of its stall samples waited on them.
+struct WaveTreeCtx {
+  const SceneDesc* sc;        // the CTA's scene descriptor (shared memory)
+  const unsigned char* blob;  // base of the scan blob as this CTA sees it (staged or global)
+  uint2* lists;               // the tree lists
+  uint2* spill;               // ... and this CTA's continuation of each in global memory (null: none)
+  int spill_cap;
+  unsigned long long* counters;
+};
 
 struct WavePool {
   unsigned long long best64[kWavePool];  // SPHERES: {float bits of t, original object index} of the ray's winner
@@ -144,8 +165,11 @@ struct WavePool {
   int tgroups[kMaxTreeGroups];
   unsigned long long express_positions;  // leading positions of the LPT order that belong to the express CTAs
   int heavy_rate;  // hand-off threshold of this frame (FrameTuning)
+  int queue_limit;    // hand-offs stop while the ring holds this many pixels (back-pressure: reserve_heavy)
+  int handoff_pause;  // ... and are not tried again for this many rounds
   int n_express;   // express CTAs of this frame
   int tree_passes; // tree passes per round: the deepest of those trees has this many levels above its leaves
+  WaveTreeCtx tctx;
   int tl_n[3], tl_off[3], tl_cap[3];  // the tree lists (in dynamic shared memory behind the staged scene): node items of pass 0 and 1, leaf items
   int free_count;
   int pixel_dry;   // the pixel queue has run dry
@@ -205,17 +229,24 @@ PT_DEV void flat_item_scan(const Keys& sc, const FlatTrees& ft, const Group& g, 
     scan_flat_range<kSmem>(sc, ft.data, g.type, base + first, min(base + kFlatChunk, g.begin + g.count), step, ray, b);
   }
 }
-// ITEMS: one (ray, leaf) item, merged into the ray's winner.
-template <bool kSmem>
-__device__ __noinline__ void wave_run_flat(WavePool* W, KeyTable kt, FlatTrees ft, Group g, uint2 it, int first, int step) {
-  const int slot = (int)(it.x & 1023u);
+PT_DEV Ray pool_ray(const WavePool* W, int slot) {
   Ray ray;
   ray.o = v3(W->ox[slot], W->oy[slot], W->oz[slot]);
   ray.d = v3(W->dx[slot], W->dy[slot], W->dz[slot]);
   ray.tm = W->tm[slot];
+  return ray;
+}
+// ITEMS: one (ray, leaf) item, merged into the ray's winner.
+template <bool kSmem>
+__device__ __noinline__ void wave_run_flat(WavePool* W, uint2 it, int first, int step) {
+  const SceneDesc& sc = *W->tctx.sc;
+  const SceneView sv = scene_view(sc, W->tctx.blob);
+  const Group g = sv.groups()[W->tgroups[(it.x >> 10) & 7u]];
+  const int slot = (int)(it.x & 1023u);
+  const Ray ray = pool_ray(W, slot);
   Best b { kInf, -1 };
-  flat_item_scan<kSmem>(kt, ft, g, it.y, ray, first, step, b);
-  if (b.id >= 0) atomicMin(&W->best64[slot], pack_winner(b.t, key_of(kt, b.id)));
+  flat_item_scan<kSmem>(sc, flat_trees(sc, sv, g.type), g, it.y, ray, first, step, b);
+  if (b.id >= 0) atomicMin(&W->best64[slot], pack_winner(b.t, key_of(sc, b.id)));
 }
 // TREE EXPANSION (BOXES and the tree passes): test the nodes [first, first + count) of level `level` of one tree of
 // one flat group against one ray.  A crossed leaf becomes a (ray, leaf) item for ITEMS, a crossed inner node a (ray,
@@ -223,27 +254,26 @@ __device__ __noinline__ void wave_run_flat(WavePool* W, KeyTable kt, FlatTrees f
 // items of the same size spread over the whole CTA, like the (ray, chunk) items of the spheres: a depth-first walk
 // per ray leaves the lanes of a warp in loops of different lengths (measured on the 10 002-triangle mesh: 9.8 of 32
 // lanes busy, and the CTA waiting at the barrier for its deepest walk).  What does not fit a list is walked depth
-// first here and now, and folded into the ray's winner `v`.  Out of line: the hot loops of the sphere path must own
-// the instruction cache and the registers.
+// first here and now, and folded into the ray's winner `v`.
 //   node item  {slot | tree group << 10 | grazing index << 13 | level << 14, node}
 //   leaf item  {slot | tree group << 10, leaf | grazing index << 31}
 template <bool kSmem>
-__device__ __noinline__ unsigned long long wave_tree_expand(WavePool* W, uint2* lists, KeyTable kt, FlatTrees ft, Group g, uint32_t slot_tg,
-                                                            uint32_t graze, int level, int first, int count, int out_list, Ray ray,
-                                                            unsigned long long* counters, unsigned long long v) {
+PT_DEV unsigned long long tree_expand(WavePool* W, const SceneDesc& sc, const FlatTrees& ft, const Group& g, const Tree& t, uint32_t slot_tg,
+                                      uint32_t graze, int level, int first, int count, int out_list, const Ray& ray,
+                                      unsigned long long v) {
   const FlatRay fr = make_flat_ray(ft.extent, ray);
   if (graze && !fr.ok) return v;  // (a ray that is not culled visits every leaf of the box tree already)
-  const Tree t = ft.trees[graze ? g.gtree : g.tree];
   const float4* boxes = ft.nodes + tree_off(t, level);
+  uint2* const lists = W->tctx.lists;
   auto test = [&](const float4* box) {
     return graze ? graze_node_bits<kSmem>(box, ray.d, fr.taud) : flat_node_bits<kSmem>(box, fr, ray, kInf);
   };
   auto leaf_here = [&](int leaf) {  // overflow: the leaf's elements, in place
-    if (counters) atomicAdd(counters + 15, 1ull);  // stats: items scanned in place
+    if (W->tctx.counters) atomicAdd(W->tctx.counters + 15, 1ull);  // stats: items scanned in place
     Best b { kInf, -1 };
-    flat_item_scan<kSmem>(kt, ft, g, (uint32_t)leaf | (graze << 31), ray, 0, 1, b);
+    flat_item_scan<kSmem>(sc, ft, g, (uint32_t)leaf | (graze << 31), ray, 0, 1, b);
     if (b.id >= 0) {
-      const unsigned long long w64 = pack_winner(b.t, key_of(kt, b.id));
+      const unsigned long long w64 = pack_winner(b.t, key_of(sc, b.id));
       if (w64 < v) v = w64;
     }
   };
@@ -261,9 +291,13 @@ __device__ __noinline__ unsigned long long wave_tree_expand(WavePool* W, uint2* 
       const int top = 31 - __clz((int)m);
       m &= ~(1u << top);
       const int node = c + (k - 1 - top);
-      if (at < W->tl_cap[dest]) {
-        lists[W->tl_off[dest] + at] = level == 0 ? make_uint2(slot_tg, (uint32_t)node | (graze << 31))
-                                                 : make_uint2(slot_tg | (graze << 13) | ((uint32_t)level << 14), (uint32_t)node);
+      if (at < W->tl_cap[dest] + W->tctx.spill_cap) {
+        const uint2 item = level == 0 ? make_uint2(slot_tg, (uint32_t)node | (graze << 31))
+                                      : make_uint2(slot_tg | (graze << 13) | ((uint32_t)level << 14), (uint32_t)node);
+        if (at < W->tl_cap[dest])
+          lists[W->tl_off[dest] + at] = item;
+        else  // (a ray along the mesh crosses hundreds of leaves: the list continues in global memory)
+          W->tctx.spill[dest * W->tctx.spill_cap + (at - W->tl_cap[dest])] = item;
       } else if (level == 0) {
         leaf_here(node);
       } else {
@@ -274,6 +308,42 @@ __device__ __noinline__ unsigned long long wave_tree_expand(WavePool* W, uint2* 
     }
   }
   return v;
+}
+// Out of line, and with scalar arguments only (WaveTreeCtx): the hot loops of the sphere path must own the instruction
+// cache and the registers.
+// BOXES: the top level of the trees [graze_from, graze_to) (0: boxes, 1: grazing index) of tree group `tg` for the ray in `slot`.
+template <bool kSmem>
+__device__ __noinline__ unsigned long long wave_tree_roots(WavePool* W, int slot, int tg, uint32_t graze_from, uint32_t graze_to, unsigned long long v) {
+  const SceneDesc& sc = *W->tctx.sc;
+  const SceneView sv = scene_view(sc, W->tctx.blob);
+  const Group g = sv.groups()[W->tgroups[tg]];
+  const FlatTrees ft = flat_trees(sc, sv, g.type);
+  const Ray ray = pool_ray(W, slot);
+#pragma unroll 1
+  for (uint32_t graze = graze_from; graze < graze_to; ++graze) {
+    const int ti = graze ? g.gtree : g.tree;
+    if (ti < 0) break;
+    const Tree t = ft.trees[ti];
+    v = tree_expand<kSmem>(W, sc, ft, g, t, (uint32_t)slot | ((uint32_t)tg << 10), graze, t.levels - 1, 0, tree_n(t, t.levels - 1), 0, ray, v);
+  }
+  return v;
+}
+// A tree pass: the children sub, sub + 1, ... (`width` of them) of one (ray, node) item.
+template <bool kSmem>
+__device__ __noinline__ void wave_tree_node_item(WavePool* W, uint2 it, int pass, int sub, int width) {
+  const SceneDesc& sc = *W->tctx.sc;
+  const SceneView sv = scene_view(sc, W->tctx.blob);
+  const int slot = (int)(it.x & 1023u);
+  const Group g = sv.groups()[W->tgroups[(it.x >> 10) & 7u]];
+  const uint32_t graze = (it.x >> 13) & 1u;
+  const int level = (int)(it.x >> 14);
+  const FlatTrees ft = flat_trees(sc, sv, g.type);
+  const Tree t = ft.trees[graze ? g.gtree : g.tree];
+  const int c0 = (int)it.y * kTreeFan + sub;
+  const int count = min(width, tree_n(t, level - 1) - c0);
+  if (count <= 0) return;
+  const unsigned long long v = tree_expand<kSmem>(W, sc, ft, g, t, it.x & 0x1fffu, graze, level - 1, c0, count, pass + 1, pool_ray(W, slot), kNoHit64);
+  if (v != kNoHit64) atomicMin(&W->best64[slot], v);
 }
 }  // namespace
 
@@ -409,6 +479,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     const int n_express = p.tuning ? min(__ldg(&p.tuning->n_express), (int)gridDim.x - 1) : p.n_express;
     W.n_express = n_express;
     W.heavy_rate = p.tuning ? __ldg(&p.tuning->heavy_rate) : kHeavyRate;
+    W.queue_limit = max(n_express, 1) * kQueuePerExpress, W.handoff_pause = 0;
     W.express_positions = p.order_mode == 1 ? min((unsigned long long)n_express * (unsigned long long)kExpressPool, p.n_positions) : 0ull;
   }
   __syncthreads();
@@ -475,8 +546,17 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     *reinterpret_cast<volatile unsigned int*>(hq.ready + (pos & (hq.cap - 1u))) = pos + hq.cap;
   };
   // Reserve a slot for a pixel that leaves: its position (write the entry, then publish_heavy()), or false: ring full.
+  // BACK-PRESSURE: a pixel is only handed off while the ring is short.  A pixel parked in a long queue makes no progress
+  // at all, and what waits when the pixel queue runs dry is the frame's tail (measured on the mesh, 256 spp: 4 916 pixels
+  // handed to 9 express CTAs waited 1.1 s on average and the frame ended 0.66 s after the queue was dry); a pixel that
+  // stays advances one bounce per round of its own CTA, and is offered again a few rounds later.
   auto reserve_heavy = [&](unsigned int& pos_out) -> bool {
+    if (*reinterpret_cast<volatile int*>(&W.handoff_pause) > 0) return false;
     unsigned int pos = ld_volatile_u32(hq.ctrl + 1);
+    if (pos - ld_volatile_u32(hq.ctrl + 0) >= (unsigned int)W.queue_limit) {
+      W.handoff_pause = kHandoffPause;
+      return false;
+    }
     for (int attempt = 0; attempt < 4; ++attempt) {
       const int dif = (int)(ld_volatile_u32(hq.ready + (pos & (hq.cap - 1u))) - pos);
       if (dif == 0) {
@@ -519,7 +599,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     // sequential scan -- closest_hit(), which knows what to do with it -- instead of burdening the phases with a test per
     // ray: such rays are one in many millions.
 #ifndef PT_X1
-    if (needs_in_order(ray)) W.in_order = 1;
+    if (needs_in_order(sc, blob_base, ray)) {
+      W.in_order = 1;
+#ifdef PT_LAST_PIXEL  // (experiments) which rays ask for the vector-order scan
+      if (p.counters && atomicAdd(p.counters + 17, 1ull) < 12ull)
+        printf("in-order ray: o %g %g %g d %g %g %g bounce %d sample %d\n", ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, bounce, sample);
+#endif
+    }
 #endif
   };
   auto load_ray = [&](int slot) -> Ray {
@@ -557,38 +643,21 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 
   // (ray, leaf) items of the flat groups with a tree: flat_item_scan / wave_emit_flat above the kernel
   uint2* const tree_lists = reinterpret_cast<uint2*>(smem_stage + ((staged + 15u) & ~15u));
-  auto run_flat_item = [&](const uint2 it, int first, int step) {
-    const Group g = sv.groups()[W.tgroups[(it.x >> 10) & 7u]];
-    wave_run_flat<kSmem>(&W, key_table(sc), flat_trees(sc, sv, g.type), g, it, first, step);
-  };
+  auto run_flat_item = [&](const uint2 it, int first, int step) { wave_run_flat<kSmem>(&W, it, first, step); };
   // BOXES: the top level of both trees (boxes, grazing index) of one flat group for one ray
-  auto emit_flat_items = [&](int slot, const Ray& ray, int tg, unsigned long long& v) {
-    const Group g = sv.groups()[W.tgroups[tg]];
-    const uint32_t slot_tg = (uint32_t)slot | ((uint32_t)tg << 10);
-    const FlatTrees ft = flat_trees(sc, sv, g.type);
-    const Tree t = ft.trees[g.tree];
-    v = wave_tree_expand<kSmem>(&W, tree_lists, key_table(sc), ft, g, slot_tg, 0u, t.levels - 1, 0, tree_n(t, t.levels - 1), 0, ray, p.counters, v);
-    if (g.gtree >= 0) {
-      const Tree gt = ft.trees[g.gtree];
-      v = wave_tree_expand<kSmem>(&W, tree_lists, key_table(sc), ft, g, slot_tg, 1u, gt.levels - 1, 0, tree_n(gt, gt.levels - 1), 0, ray, p.counters, v);
-    }
+  auto emit_flat_items = [&](int slot, int tg, uint32_t graze_from, uint32_t graze_to, unsigned long long& v) {
+    v = wave_tree_roots<kSmem>(&W, slot, tg, graze_from, graze_to, v);
   };
   // a tree pass: the children of one (ray, node) item
-  auto expand_node_item = [&](const uint2 it, int pass) {
-    const int slot = (int)(it.x & 1023u);
-    const Group g = sv.groups()[W.tgroups[(it.x >> 10) & 7u]];
-    const uint32_t graze = (it.x >> 13) & 1u;
-    const int level = (int)(it.x >> 14);
-    const FlatTrees ft = flat_trees(sc, sv, g.type);
-    const Tree t = ft.trees[graze ? g.gtree : g.tree];
-    const int c0 = (int)it.y * kTreeFan;
-    const unsigned long long v = wave_tree_expand<kSmem>(&W, tree_lists, key_table(sc), ft, g, it.x & 0x1fffu, graze, level - 1, c0,
-                                                         min(kTreeFan, tree_n(t, level - 1) - c0), pass + 1, load_ray(slot), p.counters, kNoHit64);
-    if (v != kNoHit64) atomicMin(&W.best64[slot], v);
-  };
+  auto expand_node_item = [&](const uint2 it, int pass, int sub, int width) { wave_tree_node_item<kSmem>(&W, it, pass, sub, width); };
 
   int mode = 0;  // 0: this CTA's share of the pixel queue (none for an express CTA); 1: hand-off service
-  if (tid == 0) wave_build_tables<kSmem, kTrees>(&W, &sc, sv.groups(), sv.trees(), p.tree_list_bytes);
+  if (tid == 0) {
+    wave_build_tables<kSmem, kTrees>(&W, &sc, sv.groups(), sv.trees(), p.tree_list_bytes);
+    if (kTrees)
+      W.tctx = WaveTreeCtx { &sc, blob_base, tree_lists, p.tree_spill ? p.tree_spill + (size_t)blockIdx.x * kTreeSpillLists * p.tree_spill_cap : nullptr,
+                             p.tree_spill ? (int)p.tree_spill_cap : 0, p.counters };
+  }
   if (tid < 8) W.counts[tid] = 0;
   if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.free_count = 0, W.pixel_dry = 0, W.service = 0, W.in_order = 0;
   __syncthreads();
@@ -713,11 +782,13 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
       continue;  // (the next write of W.service is behind the barrier at the loop top)
     }
     const int n_tgroups = kTrees ? W.n_tgroups : 0;  // flat groups with a tree in front of the first medium
-    const int units_per_ray = W.n_blocks + n_tgroups;  // short rounds: a ray's sphere chunks in blocks, its flat trees one by one
+    const int units_per_ray = W.n_blocks + 2 * n_tgroups;  // short rounds: a ray's sphere chunks in blocks, its flat trees (boxes, grazing index) one by one
     const bool fine = n <= kFineRays && W.blocks_ok && units_per_ray > 0;
 #ifdef PT_PHASE_TIMING
 #ifdef PT_PHASE_EXPRESS_ONLY  // time the express CTAs' short rounds only (the frame's critical path)
 #define PT_PHASE_WHO (express && mode == 1)
+#elif defined(PT_PHASE_TAIL_ONLY)  // ... or the regular CTAs' rounds after the pixel queue has run dry (the frame's tail)
+#define PT_PHASE_WHO (!express && mode == 0 && *reinterpret_cast<volatile int*>(&W.pixel_dry) != 0)
 #else
 #define PT_PHASE_WHO true
 #endif
@@ -757,7 +828,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         Best inl { kInf, -1 };
         unsigned long long v = kNoHit64;
         if (kTrees && fine && unit >= W.n_blocks) {  // short rounds: one flat tree of the ray
-          emit_flat_items(slot, ray, unit - W.n_blocks, v);
+          const int tu = unit - W.n_blocks;
+          emit_flat_items(slot, tu >> 1, (uint32_t)(tu & 1), (uint32_t)(tu & 1) + 1u, v);
           if (v != kNoHit64) atomicMin(&W.best64[slot], v);
           continue;
         }
@@ -823,7 +895,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
           }
         }
         if (!fine && n_tgroups != 0)
-          for (int tg = 0; tg < n_tgroups; ++tg) emit_flat_items(slot, ray, tg, v);
+          for (int tg = 0; tg < n_tgroups; ++tg) emit_flat_items(slot, tg, 0u, 2u, v);
         if (v != kNoHit64) atomicMin(&W.best64[slot], v);
       }
     }
@@ -832,9 +904,16 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     if (kTrees && !seq_round) {
       // ---- TREE PASSES: one level of the flat groups' trees per pass, one thread per (ray, node) item
       for (int pass = 0; pass < W.tree_passes; ++pass) {
-        const int n_items = min(W.tl_n[pass], W.tl_cap[pass]);
-        const uint2* const items = tree_lists + W.tl_off[pass];
-        for (int i = tid; i < n_items; i += kWaveThreads) expand_node_item(items[i], pass);
+        const int n_items = min(W.tl_n[pass], W.tl_cap[pass] + W.tctx.spill_cap);
+        auto item_at = [&](int i) { return i < W.tl_cap[pass] ? tree_lists[W.tl_off[pass] + i] : W.tctx.spill[pass * W.tctx.spill_cap + (i - W.tl_cap[pass])]; };
+        // a node item's 16 children go to as many threads as the pass can keep busy: one thread per item in a full round,
+        // up to one per child in a short one (whose cost is the per-thread chain: 16 boxes from L2, four at a time;
+        // measured on the mesh: 29 of the 41 us of an express CTA's round were BOXES and the tree passes).  Never finer than
+        // needed: one thread per child in FULL rounds costs 1.5 x (every thread repeats the item's set-up).
+        int per = 1;
+        while (per < kTreeFan && 2 * per * n_items <= kWaveThreads) per *= 2;
+        const int width = kTreeFan / per;
+        for (int w = tid; w < n_items * per; w += kWaveThreads) expand_node_item(item_at(w / per), pass, (w & (per - 1)) * width, width);
         __syncthreads();
       }
     }
@@ -842,8 +921,8 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 
     // ---- SPHERES: one thread per (ray, chunk) item, or per quarter of one
     if (!seq_round) {
-      const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving), n_f = kTrees ? min(W.tl_n[2], W.tl_cap[2]) : 0;
-      const uint2* const leaf_items = tree_lists + W.tl_off[2];
+      const int n_s = min(W.n_items_s, kWaveItemsStatic), n_m = min(W.n_items_m, kWaveItemsMoving), n_f = kTrees ? min(W.tl_n[2], W.tl_cap[2] + W.tctx.spill_cap) : 0;
+      auto leaf_item = [&](int i) { return i < W.tl_cap[2] ? tree_lists[W.tl_off[2] + i] : W.tctx.spill[2 * W.tctx.spill_cap + (i - W.tl_cap[2])]; };
 #ifdef PT_PHASE_TIMING
       if (tid == 0 && p.counters) atomicAdd(p.counters + 23, (unsigned long long)(n_s + n_m));
 #endif
@@ -852,12 +931,19 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         // moving items start at a warp boundary so that a warp runs one kind's code
         const int m_base = (n_s + 31) & ~31;
         const int fl_base = (m_base + n_m + 31) & ~31;  // (ray, leaf) items of the flat trees: one thread per leaf
+#if PT_LEAF_SUB  // one thread per (ray, leaf, element), like the short rounds
+        if (kTrees)
+          for (int w = tid; w < kFlatChunk * n_f; w += kWaveThreads) run_flat_item(leaf_item(w / kFlatChunk), w % kFlatChunk, kFlatChunk);
+        for (int i = tid; i < m_base + n_m; i += kWaveThreads) {
+          if (i >= n_s && i < m_base) continue;
+#else
         for (int i = tid; i < fl_base + n_f; i += kWaveThreads) {
           if ((i >= n_s && i < m_base) || (i >= m_base + n_m && i < fl_base)) continue;
           if (kTrees && i >= fl_base) {
-            run_flat_item(leaf_items[i - fl_base], 0, 1);
+            run_flat_item(leaf_item(i - fl_base), 0, 1);
             continue;
           }
+#endif
           const bool moving = i >= m_base;
           const uint2 it = W.items[moving ? kWaveItems - 1 - (i - m_base) : i];
           const int slot = (int)(it.x & 1023u);
@@ -884,7 +970,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
         const int fl_base = (f_base + n * n_flats + 31) & ~31;  // flat-tree items: one thread per (leaf, element)
         for (int w = tid; w < fl_base + kFlatChunk * n_f; w += kWaveThreads) {
           if (kTrees && w >= fl_base) {
-            run_flat_item(leaf_items[(w - fl_base) / kFlatChunk], (w - fl_base) % kFlatChunk, kFlatChunk);
+            run_flat_item(leaf_item((w - fl_base) / kFlatChunk), (w - fl_base) % kFlatChunk, kFlatChunk);
           } else if (w < n_quarters) {
             const int i = w / kParts;
             const bool moving = i >= n_s;
@@ -927,6 +1013,7 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
 
     // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
     if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.tl_n[0] = 0, W.tl_n[1] = 0, W.tl_n[2] = 0;  // (SHADE builds the next round's list)
+    if (tid == 0 && W.handoff_pause > 0) --W.handoff_pause;
     for (int e = tid; e < n; e += kWaveThreads) {
       const int slot = (int)W.list_a[e];
       Best best;
@@ -1010,6 +1097,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
               p.probe_cost[pixq] = scans;  // cost probe: how deep did one sample of this pixel go
             else
               pixel_finish(p, out_px, state_px, acc, rng, (float)p.spp);
+#ifdef PT_LAST_PIXEL  // (experiments) who finishes last: {ns since the start, own, service mode, |scans| / 4}
+            if (p.counters)
+              atomicMax(p.counters + 16, ((globaltimer_ns() - p.counters[1]) << 24) | ((unsigned long long)own << 23) | ((unsigned long long)mode << 22) |
+                                             (unsigned long long)min((scans >= 0 ? scans : -1 - scans) >> 2, (1 << 22) - 1));
+#endif
             new_pixel = true;
           } else {
             camera_ray(cam, px, py, (float)p.width, (float)p.height, rng, ray);
@@ -1178,7 +1270,7 @@ constexpr int kCostBins = 1024;
 __global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict__ probe_cost, int region_w, int region_h,
                                                            int tiles_x, int tiles_y, int* __restrict__ tile_order,
                                                            int* __restrict__ tile_bin, FrameTuning* __restrict__ tuning, int grid,
-                                                           int n_express_forced) {
+                                                           int n_express_forced, int probe_spp) {
   __shared__ int hist[kCostBins];
   __shared__ int start[kCostBins];
   __shared__ unsigned long long total, heavy;
@@ -1222,13 +1314,20 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict_
   __syncthreads();
   if (threadIdx.x == 0 && tuning) {
     FrameTuning t;
-    t.mean_scans_x1000 = (int)(1000ull * sum / (unsigned long long)max(n_probes, 1));
+    const unsigned long long samples = (unsigned long long)max(n_probes, 1) * (unsigned long long)max(probe_spp, 1);
+    t.mean_scans_x1000 = (int)(1000ull * sum / samples);
     t.heavy_share_x1000 = (int)(1000ull * heavy / (sum ? sum : 1ull));
-    t.max_scans = deepest;
+    // the deepest probed sample -- or, from a probe of several samples, what a pixel as deep as the deepest probed PIXEL
+    // would show in one (a deep pixel averages 0.6 of its deepest sample: the default scene's 31.5 of 50)
+    const int deepest_sample = probe_spp > 1 ? (int)((float)deepest / (0.6f * (float)probe_spp)) : deepest;
+    t.max_scans = deepest_sample;
     // a pixel is heavy when it spends more than four times the frame's average per sample (the default scene: 2.6 scans
     // per sample, rate 10); never below the default
-    t.heavy_rate = max(kHeavyRate, (int)((4ull * sum + (unsigned long long)n_probes / 2ull) / (unsigned long long)max(n_probes, 1)));
-    const float chain_over_frame = 162.f * (float)grid * (float)deepest / (fmaxf(1e-3f * (float)t.mean_scans_x1000, 1e-3f) * (float)region_w * (float)region_h);
+    t.heavy_rate = max(kHeavyRate, (int)((4ull * sum + samples / 2ull) / samples));
+#ifdef PT_FORCE_HEAVY_RATE  // (experiments)
+    t.heavy_rate = PT_FORCE_HEAVY_RATE;
+#endif
+    const float chain_over_frame = 162.f * (float)grid * (float)deepest_sample / (fmaxf(1e-3f * (float)t.mean_scans_x1000, 1e-3f) * (float)region_w * (float)region_h);
     t.n_express = n_express_forced >= 0 ? n_express_forced : express_ctas(grid, chain_over_frame);
     t.pad[0] = t.pad[1] = t.pad[2] = 0;
     *tuning = t;
@@ -1236,9 +1335,9 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const int* __restrict_
 }
 
 cudaError_t launch_tile_order(const int* probe_cost, int region_w, int region_h, int tiles_x, int tiles_y,
-                              int* tile_order, int* scratch, FrameTuning* tuning, int grid, int n_express_forced, cudaStream_t stream) {
+                              int* tile_order, int* scratch, FrameTuning* tuning, int grid, int n_express_forced, int probe_spp, cudaStream_t stream) {
   tile_order_kernel<<<1, 1024, 0, stream>>>(probe_cost, region_w, region_h, tiles_x, tiles_y, tile_order, scratch, tuning, grid,
-                                            n_express_forced);
+                                            n_express_forced, probe_spp);
   return cudaGetLastError();
 }
 int wave_grid(int device) {
@@ -1292,7 +1391,10 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
     // a scene is only staged if it leaves that much)
     const size_t pool_bytes = (sizeof(WavePool) + 127u) / 128u * 128u;
     const bool trees = p.scene.n_trees != 0u && p.scene.flat_cull != 0u;
-    constexpr long long kMinTreeListBytes = 64 << 10, kMaxTreeListBytes = 128 << 10;
+#ifndef PT_TREE_LIST_MAX_KB
+#define PT_TREE_LIST_MAX_KB 128
+#endif
+    constexpr long long kMinTreeListBytes = 64 << 10, kMaxTreeListBytes = PT_TREE_LIST_MAX_KB << 10;
     const long long room = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc) - (long long)pool_bytes;
     const long long for_scene = room - (trees ? kMinTreeListBytes : 0);
     q.staged_bytes = (long long)p.scene.stage_bytes <= for_scene ? p.scene.stage_bytes : (long long)p.scene.blob_bytes <= for_scene ? p.scene.blob_bytes : 0u;

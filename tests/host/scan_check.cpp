@@ -34,6 +34,7 @@ void fill_desc(const HostScene& h, const std::vector<unsigned char>& blob, Scene
   d.off_groups = ps.off_groups, d.off_sphere = ps.off_sphere, d.off_moving = ps.off_moving;
   d.off_rect = ps.off_rect, d.off_triangle = ps.off_triangle, d.off_box = ps.off_box;
   d.off_trees = ps.off_trees, d.off_nodes = ps.off_nodes, d.off_tree_ids = ps.off_tree_ids, d.n_trees = ps.n_trees;
+  d.off_planes = ps.off_planes, d.n_planes[0] = ps.n_planes[0], d.n_planes[1] = ps.n_planes[1], d.n_planes[2] = ps.n_planes[2];
   d.flat_extent = ps.flat_extent, d.flat_cull = 1u;
   d.n_objects = ps.n_objects;
   d.off_sphere_box = ps.off_sphere_box, d.off_moving_box = ps.off_moving_box;

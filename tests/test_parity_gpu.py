@@ -208,6 +208,23 @@ def test_config5_motion_blur_tile_at_full_spp(cport):
     assert np.array_equal(_bits(part[0]), _bits(got[3]))
 
 
+def test_config5_nan_pixel_is_the_references(cport):
+    """The full 3840x2160x4096 frame of BASELINE config 5 has exactly one non-finite pixel, (903, 1336)
+    (tools/nonfinite_pixels.py c5), and it is the REFERENCE's: some sample's scatter direction degenerates
+    and the NaN flows into the pixel's sum (render.hpp:95-104).  Parity means reproducing it -- NaN where the
+    reference has NaN, identical bits around it -- not avoiding it."""
+    w, h, spp, d = 3840, 2160, 4096, 50
+    sc, cam = scenes.motion_blur(w / h)
+    tile = abi.pt_region(902, 1335, 3, 3, 1)
+    got = R.render_region(sc, cam, w, h, spp, d, tile)
+    scans = R.stats()["scans"]
+    want, cnt = cport.render_region(sc, cam, w, h, spp, d, tile)
+    assert np.isnan(want[1, 1]).all() and np.isnan(got[1, 1]).all()
+    finite = np.isfinite(want).all(axis=2)
+    assert finite.sum() == 8 and np.array_equal(_bits(got[finite]), _bits(want[finite]))
+    assert scans == cnt.scans
+
+
 def test_scene_larger_than_shared_memory(cport):
     """A scan blob beyond the 227 KB shared-memory budget is streamed from L2 instead of staged."""
     sc, cam = scenes.triangle_mesh(16 / 9, nx=40, nz=32)  # 5 122 triangles x 48 B = 246 KB

@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out; O=gpurun_out
+{
+PT_PHASE_TIMING=1 python tools/phase_compare.py build/variants/phx.so c4 32
+PT_PHASE_TIMING=1 python tools/phase_compare.py build/variants/phx.so c1 100
+} > $O/r2_run28.log 2>&1
+cat $O/r2_run28.log

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out; O=gpurun_out
+{
+PT_PHASE_TIMING=1 python tools/phase_compare.py build/variants/pht2.so c4 32
+} > $O/r2_run32.log 2>&1
+cat $O/r2_run32.log

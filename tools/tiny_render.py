@@ -16,3 +16,18 @@ for name in ("media", "moving", "shapes"):
     s, c = scenes.ALL[name](4 / 3)
     a = R.render(s, c, 48, 36, 2, 50)
     print(name, float(a.mean()), R.stats()["scans"])
+# flat trees (breadth-first tree passes, grazing index): a 1 200-triangle mesh; the Cornell box (media, vector-order rays)
+s, c = scenes.c4_mesh(4 / 3, nx=30, nz=10)
+a = R.render(s, c, 64, 48, 2, 50)
+print("mesh with trees", float(a.mean()), R.stats()["scans"])
+s, c = scenes.cornell(1.0)
+a = R.render(s, c, 40, 40, 2, 50)
+print("cornell", float(a.mean()), R.stats()["scans"])
+# progressive rendering: two legs of one image
+if hasattr(R, "render_resume"):
+    sc, cam, _ = scenes.load_c1()
+    from path_tracer_b200 import abi
+    reg = abi.pt_region(0, 0, 64, 48, 1)
+    fb, st = R.render_resume(sc, cam, 64, 48, 0, 2, 50, reg)
+    fb, st = R.render_resume(sc, cam, 64, 48, 2, 4, 50, reg, state=st)
+    print("resume", float(fb.mean()))
