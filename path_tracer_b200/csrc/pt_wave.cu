@@ -1387,14 +1387,19 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
   if (p.kernel_kind == 0) {
     // ---- wavefront kernel: one CTA per SM, ray pool + (when it fits) the scan blob in shared memory
     // shared memory: the ray pool, and in front of it the scan blob with the side tables (else the blob alone, else nothing)
-    // and behind them, for scenes with flat trees, the lists of the breadth-first tree passes (at least kMinTreeListBytes:
-    // a scene is only staged if it leaves that much)
+    // and behind them, for scenes with flat trees, the lists of the breadth-first tree passes.  The lists continue in global
+    // memory (RenderParams::tree_spill), so they are kept SMALL: a scene that does not fit shared memory streams its nodes
+    // and triangles through L1, and every KB of shared memory is a KB less of it (the 10 002-triangle mesh at 64 spp: 426 ms
+    // with 98 KB of lists, 387 with 64, 380 with 32, 385 with 16).
     const size_t pool_bytes = (sizeof(WavePool) + 127u) / 128u * 128u;
     const bool trees = p.scene.n_trees != 0u && p.scene.flat_cull != 0u;
 #ifndef PT_TREE_LIST_MAX_KB
-#define PT_TREE_LIST_MAX_KB 128
+#define PT_TREE_LIST_MAX_KB 32
 #endif
-    constexpr long long kMinTreeListBytes = 64 << 10, kMaxTreeListBytes = PT_TREE_LIST_MAX_KB << 10;
+#ifndef PT_TREE_LIST_MIN_KB
+#define PT_TREE_LIST_MIN_KB 32
+#endif
+    constexpr long long kMinTreeListBytes = PT_TREE_LIST_MIN_KB << 10, kMaxTreeListBytes = PT_TREE_LIST_MAX_KB << 10;
     const long long room = (long long)max_smem_blob_bytes(device) - (long long)sizeof(SceneDesc) - (long long)pool_bytes;
     const long long for_scene = room - (trees ? kMinTreeListBytes : 0);
     q.staged_bytes = (long long)p.scene.stage_bytes <= for_scene ? p.scene.stage_bytes : (long long)p.scene.blob_bytes <= for_scene ? p.scene.blob_bytes : 0u;
