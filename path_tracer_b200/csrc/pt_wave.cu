@@ -83,9 +83,6 @@ namespace {
 #ifndef PT_HEAVY_RATE
 #define PT_HEAVY_RATE 10
 #endif
-#ifndef PT_HEAVY_RATE_DRY
-#define PT_HEAVY_RATE_DRY 10
-#endif
 #ifndef PT_EXPRESS_POOL
 #define PT_EXPRESS_POOL 64
 #endif
@@ -96,7 +93,6 @@ constexpr int kWaveThreads = PT_WAVE_THREADS;
 constexpr int kWavePool = PT_WAVE_ROUNDS * kWaveThreads;  // pixels (rays) a CTA keeps in flight: whole scan passes
 constexpr int kWaveKinds = 6;                              // 0 = background, 1 + PT_MAT_* otherwise
 constexpr int kHeavyRate = PT_HEAVY_RATE;                  // heavy: more than kHeavyBase + rate * samples scans so far
-constexpr int kHeavyRateDry = PT_HEAVY_RATE_DRY;           // ... a lower bar once the pixel queue is dry (load sharing)
 constexpr int kHeavyBase = 64;
 constexpr int kExpressPool = PT_EXPRESS_POOL;              // rays in flight in a CTA that serves the hand-off queue
 constexpr int kWaveItems = PT_WAVE_ITEMS;                  // (ray, chunk) items per round; the overflow is scanned in place
