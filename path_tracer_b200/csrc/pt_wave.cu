@@ -111,6 +111,9 @@ constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in ru
 #ifndef PT_QUEUE_PER_EXPRESS
 #define PT_QUEUE_PER_EXPRESS 16
 #endif
+#ifndef PT_TREE_FN
+#define PT_TREE_FN __noinline__
+#endif
 constexpr int kQueuePerExpress = PT_QUEUE_PER_EXPRESS;  // waiting pixels per express CTA beyond which nobody hands off
 constexpr int kHandoffPause = 8;
 constexpr int kMaxBoxBlocks = 64;
@@ -234,7 +237,7 @@ PT_DEV Ray pool_ray(const WavePool* W, int slot) {
 }
 // ITEMS: one (ray, leaf) item, merged into the ray's winner.
 template <bool kSmem>
-__device__ __noinline__ void wave_run_flat(WavePool* W, uint2 it, int first, int step) {
+__device__ PT_TREE_FN void wave_run_flat(WavePool* W, uint2 it, int first, int step) {
   const SceneDesc& sc = *W->tctx.sc;
   const SceneView sv = scene_view(sc, W->tctx.blob);
   const Group g = sv.groups()[W->tgroups[(it.x >> 10) & 7u]];
@@ -309,7 +312,7 @@ PT_DEV unsigned long long tree_expand(WavePool* W, const SceneDesc& sc, const Fl
 // cache and the registers.
 // BOXES: the top level of the trees [graze_from, graze_to) (0: boxes, 1: grazing index) of tree group `tg` for the ray in `slot`.
 template <bool kSmem>
-__device__ __noinline__ unsigned long long wave_tree_roots(WavePool* W, int slot, int tg, uint32_t graze_from, uint32_t graze_to, unsigned long long v) {
+__device__ PT_TREE_FN unsigned long long wave_tree_roots(WavePool* W, int slot, int tg, uint32_t graze_from, uint32_t graze_to, unsigned long long v) {
   const SceneDesc& sc = *W->tctx.sc;
   const SceneView sv = scene_view(sc, W->tctx.blob);
   const Group g = sv.groups()[W->tgroups[tg]];
@@ -326,7 +329,7 @@ __device__ __noinline__ unsigned long long wave_tree_roots(WavePool* W, int slot
 }
 // A tree pass: the children sub, sub + 1, ... (`width` of them) of one (ray, node) item.
 template <bool kSmem>
-__device__ __noinline__ void wave_tree_node_item(WavePool* W, uint2 it, int pass, int sub, int width) {
+__device__ PT_TREE_FN void wave_tree_node_item(WavePool* W, uint2 it, int pass, int sub, int width) {
   const SceneDesc& sc = *W->tctx.sc;
   const SceneView sv = scene_view(sc, W->tctx.blob);
   const int slot = (int)(it.x & 1023u);
