@@ -79,10 +79,19 @@ namespace ptb {
 // constant_medium's hit / pass decision or a dielectric's reflect / refract decision a few times per million.
 // Out-of-line (one copy in the kernel image; the scan loop must own the instruction cache) and by value (nothing
 // forced into local memory).
+#ifndef PT_MATH_FN_SINCOS
+#define PT_MATH_FN_SINCOS __noinline__
+#endif
+#ifndef PT_MATH_FN_POW
+#define PT_MATH_FN_POW __noinline__
+#endif
+#ifndef PT_MATH_FN_REST
+#define PT_MATH_FN_REST __noinline__
+#endif
 #ifndef PT_MATH_BINARY64  // (experiments: the round-1 evaluation of all of them)
-static __device__ __noinline__ float t_sin(float x) { return g_sinf(x); }
+static __device__ PT_MATH_FN_SINCOS float t_sin(float x) { return g_sinf(x); }
 PT_DEV float t_cos(float x) { return g_cosf(x); }
-static __device__ __noinline__ float2 t_sincos2(float x) { return make_float2(g_sinf(x), g_cosf(x)); }
+static __device__ PT_MATH_FN_SINCOS float2 t_sincos2(float x) { return make_float2(g_sinf(x), g_cosf(x)); }
 #else
 static __device__ __noinline__ float t_sin(float x) { return __double2float_rn(sin((double)x)); }
 PT_DEV float t_cos(float x) { return __double2float_rn(cos((double)x)); }
@@ -97,20 +106,20 @@ PT_DEV void t_sincos(float x, float& s, float& c) {
   s = r.x, c = r.y;
 }
 #ifndef PT_MATH_BINARY64
-static __device__ __noinline__ float t_asin(float x) { return g_asinf(x); }
-static __device__ __noinline__ float t_atan2(float y, float x) { return g_atan2f(y, x); }
+static __device__ PT_MATH_FN_REST float t_asin(float x) { return g_asinf(x); }
+static __device__ PT_MATH_FN_REST float t_atan2(float y, float x) { return g_atan2f(y, x); }
 #else
 PT_DEV float t_asin(float x) { return __double2float_rn(asin((double)x)); }
 PT_DEV float t_atan2(float y, float x) { return __double2float_rn(atan2((double)y, (double)x)); }
 #endif
 #ifndef PT_MATH_BINARY64
-static __device__ __noinline__ float t_log(float x) { return g_logf(x); }
+static __device__ PT_MATH_FN_REST float t_log(float x) { return g_logf(x); }
 #else
 static __device__ __noinline__ float t_log(float x) { return __double2float_rn(log((double)x)); }
 #endif
 // pow(x, 5.0f) (material.hpp:65)
 #ifndef PT_MATH_BINARY64
-static __device__ __noinline__ float t_pow5(float x) { return g_pow5(x); }
+static __device__ PT_MATH_FN_POW float t_pow5(float x) { return g_pow5(x); }
 #else
 PT_DEV float t_pow5(float x) {  // x^5 by binary64 products (4 roundings at 2^-53)
   const double d = (double)x;

@@ -111,8 +111,11 @@ constexpr int kFineQuarter = 4;          // ... SPHERES: a chunk's spheres in ru
 #ifndef PT_QUEUE_PER_EXPRESS
 #define PT_QUEUE_PER_EXPRESS 16
 #endif
+// The tree functions below exist in the kTrees = true instantiations only (scenes without flat trees never pay for them).
+// Inlined there: out of line they cost the mesh frame 9 % (382 -> 351 ms at 64 spp) -- a call saves and restores the
+// caller's registers through local memory, and the mesh kernel's L1 is busy with nodes and triangles.
 #ifndef PT_TREE_FN
-#define PT_TREE_FN __noinline__
+#define PT_TREE_FN __forceinline__
 #endif
 constexpr int kQueuePerExpress = PT_QUEUE_PER_EXPRESS;  // waiting pixels per express CTA beyond which nobody hands off
 constexpr int kHandoffPause = 8;
@@ -308,8 +311,7 @@ PT_DEV unsigned long long tree_expand(WavePool* W, const SceneDesc& sc, const Fl
   }
   return v;
 }
-// Out of line, and with scalar arguments only (WaveTreeCtx): the hot loops of the sphere path must own the instruction
-// cache and the registers.
+// (Scalar arguments only, the context in shared memory -- WaveTreeCtx -- so that -DPT_TREE_FN=__noinline__ stays cheap.)
 // BOXES: the top level of the trees [graze_from, graze_to) (0: boxes, 1: grazing index) of tree group `tg` for the ray in `slot`.
 template <bool kSmem>
 __device__ PT_TREE_FN unsigned long long wave_tree_roots(WavePool* W, int slot, int tg, uint32_t graze_from, uint32_t graze_to, unsigned long long v) {
