@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out; O=gpurun_out
+{
+for v in path_tracer_b200/lib/libptb200.so build/variants/tp512.so build/variants/tp768.so build/variants/tp896.so; do python tools/variant_time.py $v c4 64 3; done
+} > $O/r2_run46.log 2>&1
+cat $O/r2_run46.log
