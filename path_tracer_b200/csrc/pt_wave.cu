@@ -1444,11 +1444,10 @@ cudaError_t launch_render(const RenderParams& p, int device, int grid_override, 
       const unsigned long long sh = (q.n_positions + (unsigned long long)grid - 1ull) / (unsigned long long)grid;
       q.pool_cap = (int)(sh < 32ull ? 32ull : (sh > (unsigned long long)kWavePool ? (unsigned long long)kWavePool : sh));
     }
-#ifndef PT_TREE_POOL
-#define PT_TREE_POOL 640
-#endif
-    // (scenes with flat trees: fewer rays in flight, so that the (ray, node) and (ray, leaf) items of a round fit the tree lists)
+#ifdef PT_TREE_POOL  // (experiments.  While the tree lists lived in shared memory alone, fewer rays in flight -- 640 -- kept
+    // a round's items inside them; since they continue in global memory the full pool is faster again: 341 vs 351 ms on the mesh)
     if (trees && q.pool_cap > PT_TREE_POOL) q.pool_cap = PT_TREE_POOL;
+#endif
     // pixel-order permutation pos -> (pos * scramble) mod pixels: a multiplier near pixels / golden ratio,
     // made coprime with the pixel count so that it is a bijection
     unsigned long long mul = (unsigned long long)((double)pixels * 0.6180339887498949) | 1ull;
