@@ -644,6 +644,13 @@ int pt_debug_set_express(int n) {
 // out[0] = queue-dry - start, out[1] = last-warp-retired - start.
 // out[5..9]: hand-off service: rounds, ray-rounds, total and longest wait in the queue (ns), longest stay (rounds);
 // out[10]: (ray, chunk) items that did not fit the item list and were scanned in place
+// Tree-list items of the last launch that continued in global memory (RenderParams::tree_spill).
+int pt_debug_tree_spilled(pt_device_scene* scene, unsigned long long* out) {
+  PT_CUDA(cudaSetDevice(scene->device));
+  PT_CUDA(cudaDeviceSynchronize());
+  PT_CUDA(cudaMemcpy(out, scene->counters + 10, sizeof *out, cudaMemcpyDeviceToHost));
+  return PT_OK;
+}
 int pt_debug_timeline(pt_device_scene* scene, unsigned long long out[11]) {
   PT_CUDA(cudaSetDevice(scene->device));
   PT_CUDA(cudaDeviceSynchronize());

@@ -1013,6 +1013,11 @@ __global__ void __launch_bounds__(kWaveThreads, PT_WAVE_BLOCKS_PER_SM) render_wa
     PT_PHASE(1)
 
     // ---- LATE: the groups from the first constant_medium on; what happens next to the ray
+    if (kTrees && tid == 0 && p.counters) {  // stats: tree-list items of this round that went to global memory (tests check that it happens)
+      int spilled = 0;
+      for (int k = 0; k < 3; ++k) spilled += max(0, min(W.tl_n[k], W.tl_cap[k] + W.tctx.spill_cap) - W.tl_cap[k]);
+      if (spilled) atomicAdd(p.counters + 10, (unsigned long long)spilled);
+    }
     if (tid == 0) W.n_next = 0, W.n_own = 0, W.n_items_s = 0, W.n_items_m = 0, W.tl_n[0] = 0, W.tl_n[1] = 0, W.tl_n[2] = 0;  // (SHADE builds the next round's list)
     if (tid == 0 && W.handoff_pause > 0) --W.handoff_pause;
     for (int e = tid; e < n; e += kWaveThreads) {

@@ -549,6 +549,32 @@ def test_config4_mesh_tiles_at_full_spp(cport):
         assert scans == cnt.scans
 
 
+def test_tree_lists_spill_to_global_memory(cport):
+    """A frame with a full ray pool over the mesh: the (ray, node) / (ray, leaf) items of a round do not fit the 32 KB of
+    shared-memory lists and continue in global memory -- and nothing is walked in place.  Rows against the oracle."""
+    import ctypes as C
+    import torch
+    w, h, spp, d = 640, 360, 4, 50
+    sc, cam = scenes.c4_mesh(w / h)
+    ds = R.DeviceScene(sc, 0)
+    fb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
+    ds.render_region(cam, w, h, spp, d, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    L = R.lib()
+    spilled = C.c_ulonglong(0)
+    L.pt_debug_tree_spilled.argtypes = [C.c_void_p, C.c_void_p]
+    assert L.pt_debug_tree_spilled(ds._h, C.byref(spilled)) == 0
+    tl = (C.c_ulonglong * 11)()
+    L.pt_debug_timeline.argtypes = [C.c_void_p, C.c_void_p]
+    assert L.pt_debug_timeline(ds._h, tl) == 0
+    assert spilled.value > 100_000 and tl[10] == 0, (spilled.value, tl[10])
+    got = fb.cpu().numpy()
+    ds.close()
+    rows = R.rows_region(w, h, 5, 45)  # rows 5, 50, 95, ...
+    want, cnt = cport.render_region(sc, cam, w, h, spp, d, rows)
+    assert np.array_equal(_bits(got[5::45]), _bits(want))
+
+
 def test_config4_culling_pays(cport):
     """Config 4 at reduced size: the trees must make the frame at least 10x faster than testing every triangle."""
     w, h, spp = 480, 270, 2

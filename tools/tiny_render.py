@@ -20,6 +20,9 @@ for name in ("media", "moving", "shapes"):
 s, c = scenes.c4_mesh(4 / 3, nx=30, nz=10)
 a = R.render(s, c, 64, 48, 2, 50)
 print("mesh with trees", float(a.mean()), R.stats()["scans"])
+if os.environ.get("PT_TINY_LPT"):  # enough rays per CTA for the tree lists to spill into global memory
+    a = R.render(s, c, 480, 300, 2, 50)
+    print("mesh with trees, full pools (tree lists spill)", float(a.mean()), R.stats()["scans"])
 s, c = scenes.cornell(1.0)
 a = R.render(s, c, 40, 40, 2, 50)
 print("cornell", float(a.mean()), R.stats()["scans"])
