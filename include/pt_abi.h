@@ -261,6 +261,14 @@ int pt_render_resume(int width, int height, int spp_from, int spp_to, int depth,
                      const pt_scene* hitables, const pt_region* region, float* state, float* out,
                      int64_t out_row_pitch);
 
+/* The reference built with -DUSE_SINGLE_TASK (render.hpp:113-122, buildparams::use_single_task): ONE LocalPseudoRNG
+ * with its default seed for the whole image, pixels visited x-major (for x: for y:), fb[y][x] as in pt_render.
+ * Bit-identical to that build.  The mode is strictly serial -- every sample continues the stream where the previous
+ * one left it -- so it runs on ONE warp of GPU 0 (a team of lanes splits each closest-hit scan) and is slower than a
+ * host core: a drop-in for callers of that mode, not an accelerated path. */
+int pt_render_single_task(int width, int height, int spp, int depth, const pt_camera* camera, const pt_scene* hitables,
+                          float* fb);
+
 /* Counters accumulated by launches on this device scene since the last reset
  * (paths, scans only; synchronises the device). */
 int pt_scene_read_counters(pt_device_scene* scene, uint64_t* paths, uint64_t* scans, int reset);

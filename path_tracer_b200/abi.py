@@ -84,5 +84,5 @@ EXPORTED_SYMBOLS = [
     "pt_render", "render", "pt_render_region", "pt_last_error", "pt_abi_version", "pt_device_count",
     "pt_set_num_gpus", "pt_get_num_gpus", "pt_get_stats", "pt_scene_upload", "pt_scene_free",
     "pt_render_region_device", "pt_scene_read_counters", "pt_scene_launch_count", "pt_fb_alloc", "pt_fb_free", "pt_fb_export",
-    "pt_fb_open", "pt_fb_close", "pt_measure_fp32_peak", "pt_render_resume", "pt_render_resume_device",
+    "pt_fb_open", "pt_fb_close", "pt_measure_fp32_peak", "pt_render_resume", "pt_render_resume_device", "pt_render_single_task",
 ]

@@ -29,6 +29,7 @@ int g_cull_enabled = 1;
 int g_lpt_enabled = 1;  // pt_debug_set_lpt
 int g_n_express = -1;   // < 0: automatic (pt_debug_set_express)
 int g_kernel_kind = 0;  // 0 = wavefront kernel, 1 = lane kernel (pt_debug_set_kernel)
+bool g_single_task = false;  // set for the duration of pt_render_single_task()
 int g_fb_stage_enabled = 1;  // pt_debug_set_fb_stage: 0 = scalar stores straight into the caller's framebuffer
 pt_stats g_stats {};
 
@@ -387,7 +388,7 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   // Vectorised framebuffer stores: finished pixels go to a float4 staging image with one 16-byte store each, and a
   // resolve pass packs them into the caller's rows with coalesced 16-byte stores.  Needs 16-byte aligned rows of a
   // multiple of 4 pixels; anything else keeps the scalar stores.
-  const bool staged_fb = g_fb_stage_enabled && region->w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
+  const bool staged_fb = g_fb_stage_enabled && !g_single_task && region->w % 4 == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
                          (out_row_pitch * (long long)sizeof(float)) % 16 == 0;
   if (staged_fb) {
     const size_t need = (size_t)region->w * region->h * 4 * sizeof(float);
@@ -418,7 +419,7 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   p.state = d_state, p.state_row_pitch = state_row_pitch, p.spp_from = spp_from;
   p.counters = scene->counters;
   p.team_size = g_team_size_override;  // 0 = chosen from the pixel count at launch
-  p.kernel_kind = g_kernel_kind;
+  p.kernel_kind = g_single_task ? 1 : g_kernel_kind;
   p.pool_cap = 0;
   p.scramble = 1;
   p.n_express = g_n_express;
@@ -446,7 +447,8 @@ int pt_render_resume_device(const pt_device_scene* cscene, int width, int height
   // where the mean is 2.3) shows in one probe sample with probability 1/2, and every such pixel that the order misses
   // starts late and ends the frame with its whole serial chain.
   const unsigned long long pixels = (unsigned long long)region->w * (unsigned long long)region->h;
-  if (g_lpt_enabled && pixels >= 32768ull && spp - spp_from >= 8) {
+  if (g_single_task) p.order_mode = 3;  // render.hpp:113-122: one generator for the whole image, x-major (pt_lane.cu)
+  if (g_lpt_enabled && !g_single_task && pixels >= 32768ull && spp - spp_from >= 8) {
     const int pw = (region->w + kProbeStep - 1) / kProbeStep, ph = (region->h + kProbeStep - 1) / kProbeStep;
     const int tiles_x = (region->w + kTile - 1) / kTile, tiles_y = (region->h + kTile - 1) / kTile;
     const size_t need = (size_t)pw * ph + 2 * (size_t)tiles_x * tiles_y + sizeof(FrameTuning) / sizeof(int);
@@ -776,6 +778,17 @@ int pt_render_resume(int width, int height, int spp_from, int spp_to, int depth,
   if (rc == PT_OK) rc = pt_scene_read_counters(ds, nullptr, nullptr, 0);
   cudaFree(d_state);
   pt_scene_free(ds);
+  return rc;
+}
+
+// The reference built with -DUSE_SINGLE_TASK (render.hpp:113-122).  One warp on GPU 0: see pt_lane.cu.
+int pt_render_single_task(int width, int height, int spp, int depth, const pt_camera* camera, const pt_scene* hitables, float* fb) {
+  if (!hitables || !camera || !fb) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render_single_task: null argument");
+  if (width <= 0 || height <= 0 || spp <= 0) return fail(PT_ERR_INVALID_ARGUMENT, "pt_render_single_task: width, height and spp must be positive");
+  const pt_region full = rows_of(width, height, 0, 1);
+  g_single_task = true;
+  const int rc = pt_render_region(width, height, spp, depth, camera, hitables, &full, fb, (int64_t)width * 3);
+  g_single_task = false;
   return rc;
 }
 

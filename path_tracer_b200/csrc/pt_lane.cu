@@ -140,6 +140,46 @@ PT_DEV void lane_loop(const RenderParams& p, const SceneDesc& sc, const SceneVie
 
 }
 
+// ---------------------------------------------------------------- USE_SINGLE_TASK (render.hpp:113-122)
+// The reference's FPGA-style executor: ONE generator with the default seed for the whole image, pixels visited x-major,
+// every sample continuing the stream where the previous one left it.  The chain is strictly serial -- width x height x
+// spp samples, each consuming a data-dependent number of draws -- so all a GPU can offer is one warp: a team of 16 lanes
+// that splits every closest-hit scan (the other 16 lanes idle along in the shuffles).  Bit-identical to the reference
+// built with -DUSE_SINGLE_TASK; about 6 us per bounce, i.e. slower than one host core.  It exists so that a caller of
+// that mode has a drop-in, not because it is fast.
+template <bool kSmem>
+PT_DEV void single_task_loop(const RenderParams& p, const SceneDesc& sc, const SceneView& sv, unsigned int& n_scans) {
+  const int lane = (int)(threadIdx.x & 31u);
+  const bool act = lane < kSphereChunk;
+  const int member = lane & (kSphereChunk - 1);
+  const float fwidth = (float)p.width, fheight = (float)p.height;
+  Rng rng { 2463534242u };  // LocalPseudoRNG's default seed (rtweekend.hpp:35, xorshift.hpp)
+  for (int x = 0; x != p.width; ++x)
+    for (int y = 0; y != p.height; ++y) {
+      V3 acc = v3(0.f, 0.f, 0.f);
+      for (int s = 0; s < p.spp; ++s) {  // render.hpp:95-101
+        Ray ray;
+        camera_ray(p.cam, x, y, fwidth, fheight, rng, ray);
+        V3 att = v3(1.f, 1.f, 1.f);
+        int bounce = 0;
+        for (;;) {
+          const Best best = closest_hit<kSmem>(sc, sv, ray, rng, act, member, kSphereChunk);
+          if (lane == 0) ++n_scans;
+          V3 contribution;
+          if (shade(sc, sv, p.depth, kSmem, best, ray, rng, att, bounce, contribution)) {
+            acc = vadd(acc, contribution);
+            break;
+          }
+        }
+      }
+      if (lane == 0) {  // render.hpp:102-105
+        float* out = p.out + (long long)y * p.out_row_pitch + 3ll * x;
+        const V3 fin = vdivs(acc, (float)p.spp);
+        out[0] = fin.x, out[1] = fin.y, out[2] = fin.z;
+      }
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <bool kSmem>
 __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(const RenderParams p) {
@@ -168,7 +208,12 @@ __global__ void __launch_bounds__(kBlockThreads, kMinBlocksPerSM) render_kernel(
 
   if (p.counters && threadIdx.x == 0 && blockIdx.x == 0) atomicMin(p.counters + 1, globaltimer_ns());
   unsigned int n_scans = 0;
-  lane_loop<kSmem>(p, sc, sv, p.team_size, n_scans);
+  if (p.order_mode == 3) {  // USE_SINGLE_TASK: one warp of one CTA
+    if (blockIdx.x != 0 || threadIdx.x >= 32u) return;
+    single_task_loop<kSmem>(p, sc, sv, n_scans);
+  } else {
+    lane_loop<kSmem>(p, sc, sv, p.team_size, n_scans);
+  }
 
   if (p.counters && (threadIdx.x & 31) == 0) atomicMax(p.counters + 3, globaltimer_ns());  // timeline: warp retired
   // work counters: one atomic per warp
@@ -229,6 +274,8 @@ cudaError_t launch_lane(const RenderParams& p, int device, int grid_override, cu
   const unsigned long long pixels = (unsigned long long)p.region.w * (unsigned long long)p.region.h;
   if (p.order_mode == 1)
     q.n_positions = (unsigned long long)p.tiles_x * (unsigned long long)p.tiles_y * (unsigned long long)(kTile * kTile);
+  else if (p.order_mode == 3)
+    q.n_positions = pixels;  // (USE_SINGLE_TASK: no queue)
   else
     q.n_positions = pixels, q.order_mode = 0, q.scramble = 1ull;  // row-major
   const bool smem = (int)p.scene.blob_bytes <= max_smem_blob_bytes(device);
@@ -244,6 +291,7 @@ cudaError_t launch_lane(const RenderParams& p, int device, int grid_override, cu
   if (per_sm < 1) per_sm = 1;
   if (per_sm > kMaxBlocksPerSM) per_sm = kMaxBlocksPerSM;
   int grid = grid_override > 0 ? grid_override : sms * per_sm;
+  if (p.order_mode == 3) grid = 1;
   // Lanes per pixel at launch: one in the normal case; with fewer than kMinPixelsPerTeam pixels per
   // team (a small region, or an image strongly scaled over many GPUs) the teams start larger.
   if (q.team_size <= 0) {

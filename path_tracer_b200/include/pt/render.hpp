@@ -35,7 +35,11 @@ constexpr int output_height = OUTPUT_HEIGHT;
 #else
 constexpr int output_height = 480;
 #endif
+#ifdef USE_SINGLE_TASK  // build_parameters.hpp:5-9 (CMake option USE_SINGLE_TASK)
+constexpr bool use_single_task = true;
+#else
 constexpr bool use_single_task = false;
+#endif
 }  // namespace buildparams
 
 namespace pt {
@@ -49,6 +53,11 @@ inline void render_runtime(int width, int height, int samples, int depth, sycl::
   if (const char* n = std::getenv("PT_NUM_GPUS"))
     if (pt_set_num_gpus(std::atoi(n)) != PT_OK) throw std::runtime_error(std::string("pt_set_num_gpus: ") + pt_last_error());
   static_assert(sizeof(color) == 3 * sizeof(float));
+  if constexpr (buildparams::use_single_task) {  // render.hpp:113-122: one generator for the whole image, x-major
+    if (pt_render_single_task(width, height, samples, depth, &abi_cam, &view, reinterpret_cast<float*>(frame_buf.data())) != PT_OK)
+      throw std::runtime_error(std::string("pt_render_single_task: ") + pt_last_error());
+    return;
+  }
   if (pt_render(width, height, samples, depth, &abi_cam, &view, reinterpret_cast<float*>(frame_buf.data())) != PT_OK)
     throw std::runtime_error(std::string("pt_render: ") + pt_last_error());
 }

@@ -47,6 +47,7 @@ def lib():
         L.pt_render_region_device.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p]
         L.pt_render_resume_device.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.pt_render_resume.argtypes = [C.c_int] * 5 + [C.c_void_p] * 5 + [C.c_int64]
+        L.pt_render_single_task.argtypes = [C.c_int] * 4 + [C.c_void_p] * 3
         L.pt_scene_read_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.pt_scene_launch_count.argtypes = [C.c_void_p, C.c_void_p]
         L.pt_get_stats.argtypes = [C.c_void_p]
@@ -100,6 +101,16 @@ def render_region(scene, camera, width, height, spp, depth, region):
     out = np.zeros((region.h, region.w, 3), dtype=np.float32)
     _check(lib().pt_render_region(width, height, spp, depth, C.addressof(cam), C.addressof(s), C.addressof(region),
                                   out.ctypes.data, region.w * 3))
+    return out
+
+
+def render_single_task(scene, camera, width, height, spp, depth=50):
+    """The reference's USE_SINGLE_TASK executor (render.hpp:113-122) through pt_render_single_task: one generator for the
+    whole image, pixels x-major.  Serial by construction: small images only."""
+    s, keep = scene.as_c()
+    cam = camera_c(camera)
+    out = np.empty((height, width, 3), dtype=np.float32)
+    _check(lib().pt_render_single_task(width, height, spp, depth, C.addressof(cam), C.addressof(s), out.ctypes.data))
     return out
 
 

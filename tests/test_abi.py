@@ -52,6 +52,13 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(R.PathTracerError) as e:
         R.render(sc, cam, 8, 8, 1, 50)
     assert e.value.code == abi.PT_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    with pytest.raises(R.PathTracerError) as e:
+        R.render_single_task(sc, cam, 8, 8, 1, 50)
+    assert e.value.code == abi.PT_ERR_NO_DEVICE
+    from path_tracer_b200 import abi as A
+    with pytest.raises(R.PathTracerError) as e:
+        R.render_resume(sc, cam, 8, 8, 0, 1, 50, A.pt_region(0, 0, 8, 8, 1))
+    assert e.value.code == abi.PT_ERR_NO_DEVICE
     with pytest.raises(R.PathTracerError):
         R.DeviceScene(sc, 0)
     with pytest.raises(R.PathTracerError):

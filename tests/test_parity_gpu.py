@@ -8,6 +8,8 @@ reference's order and sin / cos / log / pow / asin / atan2 are glibc's own algor
 tests/test_glibc_math.py), so these tests require EVERY pixel to be BIT-identical to the oracle's (NaN for NaN)
 and the closest-hit scan counts to be EXACTLY equal.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -547,6 +549,31 @@ def test_config4_mesh_tiles_at_full_spp(cport):
         want, cnt = cport.render_region(sc, cam, w, h, spp, d, tile)
         assert_parity(got, want, ("config 4 tile", x0, y0))
         assert scans == cnt.scans
+
+
+def test_single_task_mode_is_the_references(cport):
+    """pt_render_single_task = the reference built with -DUSE_SINGLE_TASK (render.hpp:113-122): one generator with the
+    default seed for the whole image, pixels x-major.  Against the oracle's restatement (itself bit-identical to
+    oracle/_ref/libptref_st.so) and the committed hashes of the reference's own output."""
+    import hashlib
+    import json
+    hashes = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_hashes.json")))
+    for name, w, h, spp in (("c1", 64, 48, 4), ("shapes", 64, 48, 4), ("media", 64, 48, 4)):
+        if name == "c1":
+            sc, cam, _ = scenes.load_c1()
+        else:
+            sc, cam = scenes.ALL[name](w / h)
+        got = R.render_single_task(sc, cam, w, h, spp, 50)
+        want, cnt = cport.render_single_task(sc, cam, w, h, spp, 50)
+        assert np.array_equal(_bits(got), _bits(want)), name
+        assert R.stats()["scans"] == cnt.scans
+        assert hashlib.sha256(got.tobytes()).hexdigest() == hashes["single_task_%s_%dx%dx%dx50" % (name, w, h, spp)]
+    # a mesh with trees, and not the per-pixel-seeded image
+    sc, cam = scenes.triangle_mesh(16 / 9, nx=12, nz=6)
+    got = R.render_single_task(sc, cam, 48, 27, 2, 50)
+    want, _ = cport.render_single_task(sc, cam, 48, 27, 2, 50)
+    assert np.array_equal(_bits(got), _bits(want))
+    assert not np.array_equal(_bits(got), _bits(R.render(sc, cam, 48, 27, 2, 50)))
 
 
 def test_tree_lists_spill_to_global_memory(cport):
