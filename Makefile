@@ -35,10 +35,16 @@ oracle:
 REFERENCE ?= /root/reference
 HOST_HDRS := $(wildcard path_tracer_b200/include/pt/*.hpp path_tracer_b200/compat/*.hpp path_tracer_b200/compat/*/*.h*) include/ptscene_io.hpp
 ifneq ($(wildcard $(REFERENCE)/src/main.cpp),)
-host: build/sycl-rt-b200
+host: build/sycl-rt-b200 build/sycl-rt-b200-st
 build/sycl-rt-b200: $(REFERENCE)/src/main.cpp $(HOST_HDRS) $(LIB)
 	mkdir -p build
 	g++ -std=c++20 -O2 -ffp-contract=off -w -DOUTPUT_WIDTH=800 -DOUTPUT_HEIGHT=480 \
+	    -Ipath_tracer_b200/compat -Ipath_tracer_b200/include -Iinclude $< -o $@ \
+	    -Lpath_tracer_b200/lib -lptb200 -Wl,-rpath,'$$ORIGIN/../path_tracer_b200/lib'
+# the same application built the reference's FPGA way (CMake option USE_SINGLE_TASK), small: the mode is one serial chain
+build/sycl-rt-b200-st: $(REFERENCE)/src/main.cpp $(HOST_HDRS) $(LIB)
+	mkdir -p build
+	g++ -std=c++20 -O2 -ffp-contract=off -w -DUSE_SINGLE_TASK -DOUTPUT_WIDTH=32 -DOUTPUT_HEIGHT=24 \
 	    -Ipath_tracer_b200/compat -Ipath_tracer_b200/include -Iinclude $< -o $@ \
 	    -Lpath_tracer_b200/lib -lptb200 -Wl,-rpath,'$$ORIGIN/../path_tracer_b200/lib'
 else

@@ -44,6 +44,29 @@ def test_unmodified_main_builds_the_reference_scene(tmp_path, c1):
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
+@pytest.mark.gpu
+def test_unmodified_main_in_single_task_mode(tmp_path, cport):
+    """The reference's application compiled with -DUSE_SINGLE_TASK (CMake option USE_SINGLE_TASK, build_parameters.hpp:5-9)
+    against the host mirror: render<>() goes to pt_render_single_task, and out.png is the single-task image of the oracle
+    (one generator for the whole image, render.hpp:113-122) for the scene the binary itself built."""
+    from PIL import Image
+    binary = BINARY + "-st"
+    if not os.path.exists(binary):
+        pytest.skip("build/sycl-rt-b200-st not built (needs /root/reference at build time)")
+    dump = str(tmp_path / "scene.ptsc")
+    env = dict(os.environ, PT_IMAGE_DIR=IMAGES, PT_DUMP_SCENE=dump)
+    r = subprocess.run([binary], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    sc, cam, (w, h, spp, d) = Scene.load(dump)
+    assert (w, h, spp, d) == (32, 24, 100, 50)
+    img = np.asarray(Image.open(str(tmp_path / "out.png")).convert("RGB")).astype(np.int32)
+    want, _ = cport.render_single_task(sc, cam, w, h, spp, d)
+    want8 = (256 * np.clip(np.sqrt(want), 0.0, 0.999)).astype(np.int32)
+    assert np.array_equal(img[::-1], want8)  # (bit-identical pixels: the tone map sees the same floats)
+    par, _ = cport.render(sc, cam, w, h, spp, d)
+    assert not np.array_equal(img[::-1], (256 * np.clip(np.sqrt(par), 0.0, 0.999)).astype(np.int32))
+
+
 @needs_binary
 @pytest.mark.gpu
 def test_unmodified_main_renders_out_png(tmp_path, cport, c1):
