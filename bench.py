@@ -222,7 +222,8 @@ def run_reference_arm(args):
         cpu_sample(oracle, sc, cam, w, h, spp, d, small, False)
     t_total, paths_total, full_step = 0.0, 0, None
     for it in range(args.steps):
-        if it == 0 and oracle.kind == "reference" and hasattr(oracle, "render_full") and d == 50:
+        if it == 0 and args.workload == "c1" and oracle.kind == "reference" and hasattr(oracle, "render_full") and d == 50:
+            # (the default scene only: 21 s on 16 cores.  The whole frame of config 4 would take the CPU three hours)
             # the first timed step goes through the reference's OWN entry point, render<W,H,S>() (render.hpp:141-160),
             # on the whole frame; the others through render_pixel<> on the bounded sample
             t0 = time.perf_counter()
