@@ -242,7 +242,12 @@ int pt_scene_upload(const pt_scene* scene, int device, pt_device_scene** out);
 void pt_scene_free(pt_device_scene* scene);
 
 /* Launch on `stream` (a cudaStream_t, 0 = default), asynchronous.  d_out is a
- * DEVICE pointer (may be a peer-mapped pointer on another GPU). */
+ * DEVICE pointer (may be a peer-mapped pointer on another GPU).
+ * Concurrency: a pt_device_scene owns its pixel queue, hand-off ring, probe buffers and counters, so the launches
+ * of ONE scene must be ordered (one stream, or events between streams).  DIFFERENT scenes may be launched on
+ * different streams of one device at the same time: the render kernel is a cooperative launch (its CTAs wait for
+ * each other), so the runtime runs such launches one after the other instead of half-resident side by side --
+ * correct, never deadlocked, no overlap to be gained (tests/test_parity_gpu.py::test_concurrent_scenes_on_two_streams). */
 int pt_render_region_device(const pt_device_scene* scene, int width, int height, int spp,
                             int depth, const pt_camera* camera, const pt_region* region,
                             float* d_out, int64_t out_row_pitch, void* stream);

@@ -284,6 +284,27 @@ def test_device_resident_api_matches_host_api(c1):
     ds.close()
 
 
+def test_concurrent_scenes_on_two_streams(c1):
+    """Two device scenes launched back to back on two streams of one GPU (pt_abi.h, "Concurrency"): the CTAs of the
+    render kernel wait for each other, so two half-resident grids would hang until the watchdog; the cooperative launch
+    makes the runtime order them.  Both frames must be complete and bit-identical to a render on its own."""
+    import torch
+    sc, cam, (w, h, _, d) = c1
+    sc2, cam2 = scenes.media(w / h)
+    alone = [R.render(sc, cam, w, h, 6, d), R.render(sc2, cam2, w, h, 6, d)]
+    a, b = R.DeviceScene(sc, 0), R.DeviceScene(sc2, 0)
+    fbs = [torch.full((h, w, 3), -1.0, dtype=torch.float32, device="cuda:0") for _ in range(2)]
+    streams = [torch.cuda.Stream(device=0), torch.cuda.Stream(device=0)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for ds, c, fb, st in ((a, cam, fbs[0], streams[0]), (b, cam2, fbs[1], streams[1])):
+            ds.render_region(c, w, h, 6, d, R.rows_region(w, h, 0, 1), fb.data_ptr(), w * 3, st.cuda_stream)
+    torch.cuda.synchronize()
+    for fb, want in zip(fbs, alone):
+        assert np.array_equal(_bits(fb.cpu().numpy()), _bits(want))
+    a.close(), b.close()
+
+
 def test_single_process_multi_gpu(c1):
     if R.device_count() < 2:
         pytest.skip("needs 2 GPUs")
